@@ -407,7 +407,7 @@ def gen_gridworld(gym, out):
 
 
 def gen_gridworld_barren(gym, out):
-    """Both-barren states consume no draw: enumerate them separately (16 states x 24 actions)."""
+    """Both-barren states consume no draw: enumerate them separately (8 states x 24 actions)."""
     saved = (np.random.rand, np.random.randint)
     rp = Replay()
     try:
