@@ -1,0 +1,13 @@
+"""gym_cellular_b200 -- B200-native batched environment step for the gym-cellular environments.
+
+Host code is Python; the hot path is hand-written CUDA for sm_100a behind a C ABI
+(include/gym_cellular_b200.h, libgymcellular_b200.so) called through ctypes.  See DESIGN.md.
+"""
+from ._gym import gym  # noqa: F401  (real gymnasium, or the structural stand-in)
+from . import tables
+from .tables import right_polarizing, multiple_optima, nonlinear, nonlinear_right_polarizing
+from .vector_env import CellularVectorEnv, make_vector_env
+
+__all__ = ["CellularVectorEnv", "make_vector_env", "tables", "right_polarizing", "multiple_optima",
+           "nonlinear", "nonlinear_right_polarizing"]
+__version__ = "0.1.0"

@@ -1,0 +1,364 @@
+// C ABI of libgymcellular_b200.so (include/gym_cellular_b200.h).  No C++ exceptions cross the
+// boundary: every entry point returns a gc_status and records a thread-local message.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gc_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define GC_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(GC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+constexpr int kHostStreams = 3;
+
+// x * 2^-32 < p  <=>  x < ceil(p * 2^32)   (p * 2^32 is exact in double: a power-of-two scaling)
+unsigned long long threshold_of(double p)
+{
+    if (!(p > 0.0)) return 0ull;
+    if (p >= 1.0) return 1ull << 32;
+    return static_cast<unsigned long long>(std::ceil(p * 4294967296.0));
+}
+
+}  // namespace
+
+struct gc_env {
+    gc_config cfg;
+    CellTables tab;
+    GridParams grid;
+    bool tables_set;
+    int n_sm;
+    int64_t global_step;
+    int64_t launches;
+    unsigned long long *d_status;
+    cudaStream_t hstream[kHostStreams];
+    cudaEvent_t hevent[kHostStreams];
+    bool host_ready;
+};
+
+namespace {
+
+int check_env(const gc_env *env)
+{
+    if (!env) return fail(GC_ERR_INVALID, "env is NULL");
+    return GC_OK;
+}
+
+int check_range(const gc_env *env, int64_t begin, int64_t count)
+{
+    const int64_t n = env->cfg.n_envs;
+    if (begin < 0 || count < 0 || begin + count > n)
+        return fail(GC_ERR_INVALID, "env range [%lld, %lld) outside [0, %lld)", (long long)begin,
+                    (long long)(begin + count), (long long)n);
+    if (begin % 16 != 0)
+        return fail(GC_ERR_INVALID, "env_begin must be a multiple of 16");
+    if ((begin + count) % 16 != 0 && begin + count != n)
+        return fail(GC_ERR_INVALID, "env range must end on a multiple of 16 or at n_envs");
+    return GC_OK;
+}
+
+StepIO make_io(const gc_env *env, int64_t begin, int64_t count, const int8_t *actions, int8_t *state,
+               int32_t *t, float *reward, uint32_t *index, uint8_t *terminated, uint8_t *truncated,
+               uint8_t *unsafe, uint8_t *count_out, int8_t *se_row, const double *replay, int64_t *stats)
+{
+    StepIO io;
+    io.actions = actions; io.state = state; io.t = t; io.reward = reward; io.index = index;
+    io.terminated = terminated; io.truncated = truncated; io.unsafe = unsafe; io.count = count_out;
+    io.se_row = se_row; io.replay = replay;
+    io.stats = reinterpret_cast<unsigned long long *>(stats);
+    io.status = env->d_status;
+    io.begin = begin; io.end = begin + count; io.ld = env->cfg.ld;
+    io.env_id_offset = env->cfg.env_id_offset;
+    io.seed_lo = static_cast<uint32_t>(env->cfg.seed);
+    io.seed_hi = static_cast<uint32_t>(env->cfg.seed >> 32);
+    io.rng_counter = static_cast<uint32_t>(env->global_step);
+    io.episodic = (env->cfg.flags & GC_F_RNG_EPISODIC) ? 1 : 0;
+    io.max_episode_steps = env->cfg.max_episode_steps;
+    return io;
+}
+
+int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
+{
+    if (io.end <= io.begin) return GC_OK;
+    cudaError_t e;
+    if (env->cfg.kind == GC_KIND_CELLULAR) {
+        const int mode = io.replay ? GC_RNG_REPLAY : ((env->cfg.flags & GC_F_NOISE) ? GC_RNG_PHILOX : GC_RNG_NONE);
+        e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);
+    } else {
+        e = gc_launch_grid_step(env->grid, io, io.replay ? GC_RNG_REPLAY : GC_RNG_PHILOX, env->n_sm, st);
+    }
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+    env->launches += 1;
+    return GC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gc_abi_version(void) { return GC_ABI_VERSION; }
+
+const char *gc_last_error(void) { return g_err; }
+
+int gc_create(const gc_config *cfg, gc_env **out)
+{
+    if (!cfg || !out) return fail(GC_ERR_INVALID, "cfg/out is NULL");
+    if (cfg->struct_size != sizeof(gc_config))
+        return fail(GC_ERR_INVALID, "gc_config.struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(gc_config));
+    if (cfg->n_envs < 1) return fail(GC_ERR_INVALID, "n_envs must be >= 1");
+    if (cfg->ld < cfg->n_envs || cfg->ld % 16 != 0)
+        return fail(GC_ERR_INVALID, "ld must be a multiple of 16 and >= n_envs");
+    if (cfg->max_episode_steps < 0) return fail(GC_ERR_INVALID, "max_episode_steps must be >= 0");
+    if (cfg->kind == GC_KIND_CELLULAR) {
+        if (cfg->n_cells < 1 || cfg->n_cells > GC_MAX_CELLS)
+            return fail(GC_ERR_INVALID, "n_cells must be in 1..%d", GC_MAX_CELLS);
+        if (cfg->n_states < 2 || cfg->n_states > GC_MAX_LEVELS || cfg->n_actions < 1 || cfg->n_actions > GC_MAX_LEVELS)
+            return fail(GC_ERR_INVALID, "n_states must be in 2..%d and n_actions in 1..%d", GC_MAX_LEVELS, GC_MAX_LEVELS);
+        if (cfg->n_cells * std::log2((double)cfg->n_states) > 32.0 + 1e-9)
+            return fail(GC_ERR_INVALID, "n_states^n_cells does not fit the 32-bit tabular index");
+    } else if (cfg->kind == GC_KIND_GRIDWORLD) {
+        if (cfg->n_cells != 2 || cfg->n_states != 20 || cfg->n_actions != 5)
+            return fail(GC_ERR_INVALID, "grid world is 2 jurisdictions x 20 codes x 5 actions");
+    } else {
+        return fail(GC_ERR_INVALID, "unknown kind %d", cfg->kind);
+    }
+    int n_dev = 0;
+    GC_CUDA(cudaGetDeviceCount(&n_dev));
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(GC_ERR_INVALID, "device %d not in [0, %d)", cfg->device, n_dev);
+    GC_CUDA(cudaSetDevice(cfg->device));
+    gc_env *env = new (std::nothrow) gc_env();
+    if (!env) return fail(GC_ERR_INVALID, "out of host memory");
+    std::memset(env, 0, sizeof(*env));
+    env->cfg = *cfg;
+    GC_CUDA(cudaDeviceGetAttribute(&env->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    env->grid.dispersal_thr = threshold_of(cfg->dispersal_prob);
+    env->grid.dispersal_prob = cfg->dispersal_prob;
+    env->tables_set = (cfg->kind == GC_KIND_GRIDWORLD);
+    cudaError_t e = cudaMalloc(&env->d_status, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(env->d_status, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        delete env;
+        return fail(GC_ERR_CUDA, "status word allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = env;
+    return GC_OK;
+}
+
+int gc_destroy(gc_env *env)
+{
+    if (!env) return GC_OK;
+    cudaSetDevice(env->cfg.device);
+    if (env->host_ready)
+        for (int i = 0; i < kHostStreams; ++i) {
+            cudaStreamDestroy(env->hstream[i]);
+            cudaEventDestroy(env->hevent[i]);
+        }
+    if (env->d_status) cudaFree(env->d_status);
+    delete env;
+    return GC_OK;
+}
+
+int gc_set_tables(gc_env *env, const gc_cell_tables *t)
+{
+    if (int rc = check_env(env)) return rc;
+    if (env->cfg.kind != GC_KIND_CELLULAR) return fail(GC_ERR_INVALID, "tables apply to the cellular family only");
+    if (!t || !t->move || !t->reward || !t->side_effects || !t->counted || !t->initial_state)
+        return fail(GC_ERR_INVALID, "move, reward, side_effects, counted and initial_state are required");
+    const int C = env->cfg.n_cells, S = env->cfg.n_states, A = env->cfg.n_actions;
+    const bool noise = (env->cfg.flags & GC_F_NOISE) != 0;
+    if (noise && (!t->noisy || !t->draws)) return fail(GC_ERR_INVALID, "GC_F_NOISE needs the noisy and draws tables");
+    CellTables &tab = env->tab;
+    std::memset(&tab, 0, sizeof(tab));
+    for (int s = 0; s < S; ++s)
+        for (int a = 0; a < A; ++a) {
+            const int mv = t->move[s * A + a];
+            const int nz = t->noisy ? t->noisy[s * A + a] : mv;
+            const int dr = (noise && t->draws) ? (t->draws[s * A + a] != 0) : 0;
+            if (mv < 0 || mv >= S || nz < 0 || nz >= S)
+                return fail(GC_ERR_INVALID, "move/noisy[%d][%d] outside [0, %d)", s, a, S);
+            tab.sa[s * GC_LVL_PAD + a] = (uint32_t)mv | ((uint32_t)nz << 4) | ((uint32_t)dr << 8);
+            tab.reward[s * GC_LVL_PAD + a] = t->reward[s * A + a];
+        }
+    for (int j = 0; j < C; ++j)
+        for (int s0 = 0; s0 < S; ++s0)
+            for (int sp = 0; sp < S; ++sp) {
+                const int code = t->side_effects[(j * S + s0) * S + sp];
+                if (code < 0 || code > 2) return fail(GC_ERR_INVALID, "side_effects code %d not in {0,1,2}", code);
+                tab.se[j][s0 * GC_LVL_PAD + sp] = (uint8_t)code;
+            }
+    uint32_t place = 1, init_index = 0;
+    for (int c = 0; c < C; ++c) {
+        const int lv = t->initial_state[c];
+        if (lv < 0 || lv >= S) return fail(GC_ERR_INVALID, "initial_state[%d] outside [0, %d)", c, S);
+        tab.place[c] = place;
+        tab.init[c] = (int8_t)lv;
+        init_index += (uint32_t)lv * place;
+        place *= (uint32_t)S;
+    }
+    tab.init_index = init_index;
+    for (int s = 0; s < S; ++s) if (t->counted[s]) tab.counted_mask |= 1u << s;
+    tab.n_cells = C; tab.n_states = S; tab.n_actions = A;
+    tab.reward_log2 = (env->cfg.flags & GC_F_REWARD_LOG2) ? 1 : 0;
+    tab.noise_thr = threshold_of(env->cfg.noise_prob);
+    tab.noise_prob = env->cfg.noise_prob;
+    env->tables_set = true;
+    return GC_OK;
+}
+
+int gc_set_global_step(gc_env *env, int64_t step)
+{
+    if (int rc = check_env(env)) return rc;
+    env->global_step = step;
+    return GC_OK;
+}
+
+int64_t gc_get_global_step(const gc_env *env) { return env ? env->global_step : -1; }
+
+int64_t gc_launch_count(const gc_env *env) { return env ? env->launches : -1; }
+
+int gc_reset(gc_env *env, const uint8_t *mask, int8_t *state, int32_t *t, uint32_t *index, void *stream)
+{
+    if (int rc = check_env(env)) return rc;
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    if (!state || !t) return fail(GC_ERR_INVALID, "state/t is NULL");
+    GC_CUDA(cudaSetDevice(env->cfg.device));
+    int8_t init[GC_MAX_CELLS] = {0};
+    uint32_t init_index;
+    if (env->cfg.kind == GC_KIND_GRIDWORLD) {
+        init[0] = 15; init[1] = 18; init_index = 15 + 20 * 18;     // grid_world.py:238-259
+    } else {
+        std::memcpy(init, env->tab.init, sizeof(init));
+        init_index = env->tab.init_index;
+    }
+    // whole words are written, so cover the padded length
+    const int64_t n_pad = (env->cfg.n_envs + 3) / 4 * 4;
+    cudaError_t e = gc_launch_reset(env->cfg.n_cells, init, init_index, mask, state, t, index, n_pad,
+                                    env->cfg.ld, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "reset kernel launch failed: %s", cudaGetErrorString(e));
+    env->launches += 1;
+    return GC_OK;
+}
+
+int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *actions, int8_t *state,
+            int32_t *t, float *reward, uint32_t *index, uint8_t *terminated, uint8_t *truncated,
+            uint8_t *unsafe, uint8_t *count, int8_t *se_row, const double *replay_u, int64_t *stats,
+            void *stream)
+{
+    if (int rc = check_env(env)) return rc;
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    if (!actions || !state || !t || !reward || !index || !terminated || !truncated || !unsafe || !count)
+        return fail(GC_ERR_INVALID, "a required device pointer is NULL");
+    if (int rc = check_range(env, env_begin, env_count)) return rc;
+    GC_CUDA(cudaSetDevice(env->cfg.device));
+    const StepIO io = make_io(env, env_begin, env_count, actions, state, t, reward, index, terminated,
+                              truncated, unsafe, count, se_row, replay_u, stats);
+    if (int rc = launch_step(env, io, static_cast<cudaStream_t>(stream))) return rc;
+    if (env_begin + env_count == env->cfg.n_envs) env->global_step += 1;   // a full pass over the shard
+    return GC_OK;
+}
+
+int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h_reward,
+                 uint32_t *h_index, uint8_t *h_terminated, uint8_t *h_truncated, uint8_t *h_unsafe,
+                 uint8_t *h_count, int8_t *d_actions, int8_t *d_state, int32_t *d_t, float *d_reward,
+                 uint32_t *d_index, uint8_t *d_terminated, uint8_t *d_truncated, uint8_t *d_unsafe,
+                 uint8_t *d_count, int64_t *d_stats, int64_t chunk_envs)
+{
+    if (int rc = check_env(env)) return rc;
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    if (!h_actions || !d_actions || !d_state || !d_t || !d_reward || !d_index || !d_terminated ||
+        !d_truncated || !d_unsafe || !d_count)
+        return fail(GC_ERR_INVALID, "a required pointer is NULL");
+    GC_CUDA(cudaSetDevice(env->cfg.device));
+    if (!env->host_ready) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            GC_CUDA(cudaStreamCreateWithFlags(&env->hstream[i], cudaStreamNonBlocking));
+            GC_CUDA(cudaEventCreateWithFlags(&env->hevent[i], cudaEventDisableTiming));
+        }
+        env->host_ready = true;
+    }
+    const int64_t n = env->cfg.n_envs, ld = env->cfg.ld;
+    const int C = env->cfg.n_cells;
+    if (chunk_envs <= 0) chunk_envs = 1 << 20;
+    chunk_envs = (chunk_envs + 15) / 16 * 16;
+    int k = 0;
+    for (int64_t b = 0; b < n; b += chunk_envs, ++k) {
+        const int64_t cnt = (b + chunk_envs < n) ? chunk_envs : (n - b);
+        const int64_t cnt_pad = (cnt + 3) / 4 * 4;      // whole words; ld padding makes this safe
+        cudaStream_t st = env->hstream[k % kHostStreams];
+        GC_CUDA(cudaMemcpy2DAsync(d_actions + b, ld, h_actions + b, ld, cnt_pad, C, cudaMemcpyHostToDevice, st));
+        const StepIO io = make_io(env, b, cnt, d_actions, d_state, d_t, d_reward, d_index, d_terminated,
+                                  d_truncated, d_unsafe, d_count, nullptr, nullptr, d_stats);
+        if (int rc = launch_step(env, io, st)) return rc;
+        if (h_state) GC_CUDA(cudaMemcpy2DAsync(h_state + b, ld, d_state + b, ld, cnt, C, cudaMemcpyDeviceToHost, st));
+        if (h_reward) GC_CUDA(cudaMemcpyAsync(h_reward + b, d_reward + b, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (h_index) GC_CUDA(cudaMemcpyAsync(h_index + b, d_index + b, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (h_terminated) GC_CUDA(cudaMemcpyAsync(h_terminated + b, d_terminated + b, cnt, cudaMemcpyDeviceToHost, st));
+        if (h_truncated) GC_CUDA(cudaMemcpyAsync(h_truncated + b, d_truncated + b, cnt, cudaMemcpyDeviceToHost, st));
+        if (h_unsafe) GC_CUDA(cudaMemcpyAsync(h_unsafe + b, d_unsafe + b, cnt, cudaMemcpyDeviceToHost, st));
+        if (h_count) GC_CUDA(cudaMemcpyAsync(h_count + b, d_count + b, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kHostStreams && i < k; ++i) GC_CUDA(cudaStreamSynchronize(env->hstream[i]));
+    env->global_step += 1;
+    return GC_OK;
+}
+
+int gc_poll_status(gc_env *env, void *stream)
+{
+    if (int rc = check_env(env)) return rc;
+    GC_CUDA(cudaSetDevice(env->cfg.device));
+    unsigned long long word = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GC_CUDA(cudaMemcpyAsync(&word, env->d_status, sizeof(word), cudaMemcpyDeviceToHost, st));
+    GC_CUDA(cudaStreamSynchronize(st));
+    if (word) {
+        GC_CUDA(cudaMemsetAsync(env->d_status, 0, sizeof(word), st));
+        return fail(GC_ERR_ACTION, "'position': a grid-world action named no go-to position in any jurisdiction");
+    }
+    return GC_OK;
+}
+
+int gc_encode(int device, int64_t n, int64_t ld, int32_t n_cells, int32_t radix, const int8_t *cells,
+              uint32_t *index, void *stream)
+{
+    if (!cells || !index || n < 0 || ld < n || ld % 16 != 0 || n_cells < 1 || radix < 1)
+        return fail(GC_ERR_INVALID, "gc_encode: bad arguments");
+    GC_CUDA(cudaSetDevice(device));
+    cudaError_t e = gc_launch_encode((n + 3) / 4 * 4, ld, n_cells, (uint32_t)radix, cells, index,
+                                     static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "encode kernel launch failed: %s", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+int gc_decode(int device, int64_t n, int64_t ld, int32_t n_cells, int32_t radix, const uint32_t *index,
+              int8_t *cells, void *stream)
+{
+    if (!cells || !index || n < 0 || ld < n || ld % 16 != 0 || n_cells < 1 || radix < 1)
+        return fail(GC_ERR_INVALID, "gc_decode: bad arguments");
+    GC_CUDA(cudaSetDevice(device));
+    cudaError_t e = gc_launch_decode((n + 3) / 4 * 4, ld, n_cells, (uint32_t)radix, index, cells,
+                                     static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "decode kernel launch failed: %s", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+}  // extern "C"

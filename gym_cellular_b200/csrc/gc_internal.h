@@ -1,0 +1,71 @@
+// Internal declarations shared by the kernels (gc_kernels.cu) and the C ABI (gc_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gym_cellular_b200.h"
+
+#define GC_LVL_PAD 8                       // tables are indexed [s * GC_LVL_PAD + a]
+#define GC_TBL (GC_LVL_PAD * GC_LVL_PAD)   // 64 entries
+
+// RNG source of a launch
+enum { GC_RNG_NONE = 0, GC_RNG_PHILOX = 1, GC_RNG_REPLAY = 2 };
+
+// Per-env array pointers of one step launch (device pointers to the full arrays).
+struct StepIO {
+    const int8_t *actions;
+    int8_t       *state;
+    int32_t      *t;
+    float        *reward;
+    uint32_t     *index;
+    uint8_t      *terminated, *truncated, *unsafe, *count;
+    int8_t       *se_row;       // optional
+    const double *replay;       // optional, [n][slots]
+    unsigned long long *stats;  // optional, int64[GC_N_STATS]
+    unsigned long long *status; // handle-owned status word
+    int64_t begin, end;         // env range of this launch (end <= n_envs)
+    int64_t ld;
+    int64_t env_id_offset;
+    uint32_t seed_lo, seed_hi;
+    uint32_t rng_counter;       // global step (ignored when episodic)
+    int32_t  episodic;
+    int32_t  max_episode_steps;
+};
+
+// Constant tables of the cellular family, passed by value as a __grid_constant__ parameter and
+// staged into shared memory once per block.
+struct CellTables {
+    uint32_t sa[GC_TBL];             // bits 0-3 move, 4-7 noisy, 8 draws
+    float    reward[GC_TBL];
+    uint8_t  se[GC_MAX_CELLS][GC_TBL]; // [j][s0' * GC_LVL_PAD + s'_p]
+    uint32_t place[GC_MAX_CELLS];    // mixed-radix place values S^c (mod 2^32)
+    int8_t   init[GC_MAX_CELLS];
+    uint32_t init_index;
+    uint32_t counted_mask;           // bit l set: level l counts towards the incidence
+    int32_t  n_cells, n_states, n_actions;
+    int32_t  reward_log2;
+    unsigned long long noise_thr;    // draw fires iff word < noise_thr  (word*2^-32 < p)
+    double   noise_prob;             // for the replay path (compares doubles like the reference)
+};
+
+struct GridParams {
+    unsigned long long dispersal_thr;
+    double dispersal_prob;
+};
+
+struct LaunchGeom {
+    int blocks_per_sm_hint;
+    int n_sm;
+};
+
+cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm,
+                                cudaStream_t stream);
+cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm,
+                                cudaStream_t stream);
+cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,
+                            int8_t *state, int32_t *t, uint32_t *index, int64_t n, int64_t ld,
+                            cudaStream_t stream);
+cudaError_t gc_launch_encode(int64_t n, int64_t ld, int n_cells, uint32_t radix, const int8_t *cells,
+                             uint32_t *index, cudaStream_t stream);
+cudaError_t gc_launch_decode(int64_t n, int64_t ld, int n_cells, uint32_t radix, const uint32_t *index,
+                             int8_t *cells, cudaStream_t stream);

@@ -1,0 +1,487 @@
+// sm_100a kernels of the batched gym-cellular step.
+//
+// Layout and mapping.  Every int8 row (one cell of the state / action, [ld] envs) is moved as
+// 32-bit words: a thread owns kEPT = 4 consecutive envs, so a warp reads 128 contiguous bytes of each
+// int8 row and 512 contiguous bytes (one 128-bit access per lane) of each 32-bit per-env vector
+// (t, reward, index).  All accesses are fully coalesced, every byte is touched exactly once, and the
+// block loops grid-stride over the env range with a grid of (SM count x resident blocks).
+//
+// The work is HBM-bound integer/byte arithmetic (3C+20 bytes per env-step); there is
+// no contraction, hence no tensor-core path.  Transition / reward / side-effect tables arrive as a
+// __grid_constant__ parameter block and are staged into shared memory once per block.
+//
+// Reference behaviour implemented here (paths relative to the reference checkout):
+//   cellular step   gym_cellular/envs/cells3states3actions3.py:116-212, cells2rest3.py:103-187,
+//                   cells3resetVdeadlock.py:35-68,148-228 (via the tables built in
+//                   gym_cellular_b200/tables.py)
+//   grid world step gym_cellular/envs/grid_world.py:107-179 (closed form, see grid_step_kernel)
+//   codec           gym_cellular/envs/utils/generalized_space_transformations.py:1-23
+#include "gc_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kEPT = 4;
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, counter based: word w of env e at step t = philox(key=seed, ctr=(e_lo,e_hi,t,w/4))[w%4]
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int e) { return (w >> (8 * e)) & 0xFFu; }
+
+// streaming accesses: every byte is used once, keep it out of L1
+__device__ __forceinline__ uint32_t ld_stream_u32(const void *p)
+{
+    return __ldcs(reinterpret_cast<const unsigned int *>(p));
+}
+__device__ __forceinline__ void st_stream_u32(void *p, uint32_t v)
+{
+    __stcs(reinterpret_cast<unsigned int *>(p), v);
+}
+__device__ __forceinline__ int4 ld_stream_v4(const void *p) { return __ldcs(reinterpret_cast<const int4 *>(p)); }
+__device__ __forceinline__ void st_stream_v4(void *p, int4 v) { __stcs(reinterpret_cast<int4 *>(p), v); }
+
+// Per-thread statistics, reduced once per block at kernel exit: warp shuffles, one shared-memory
+// atomic per warp, one global atomic per block and statistic.
+struct ThreadStats {
+    unsigned long long steps, unsafe, count, truncated;
+    long long reward_q24;
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigned long long *s_stats,
+                                                  unsigned long long *g_stats)
+{
+    // s_stats zeroed before the main loop (with a __syncthreads in between)
+    unsigned long long v[5] = {ts.steps, ts.unsafe, ts.count, ts.truncated,
+                               static_cast<unsigned long long>(ts.reward_q24)};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const unsigned long long w = warp_sum(v[i]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_stats[i], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && s_stats[threadIdx.x]) atomicAdd(&g_stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cellular (polarisation family) step: C cells, per-cell identical [S][A] tables.
+template <int C, int RNG>
+__global__ void __launch_bounds__(kThreads)
+cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ StepIO io)
+{
+    __shared__ uint2 s_sa[GC_TBL];                 // .x packed move/noisy/draws, .y reward bits
+    __shared__ uint8_t s_se[C][GC_TBL];
+    __shared__ unsigned long long s_stats[5];
+
+    for (int i = threadIdx.x; i < GC_TBL; i += kThreads)
+        s_sa[i] = make_uint2(tab.sa[i], __float_as_uint(tab.reward[i]));
+    for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads)
+        s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    ThreadStats ts = {0, 0, 0, 0, 0};
+    const int64_t ld = io.ld;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+         e0 < io.end; e0 += stride) {
+        uint32_t sw[C], aw[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            sw[c] = ld_stream_u32(io.state + c * ld + e0);
+            aw[c] = ld_stream_u32(io.actions + c * ld + e0);
+        }
+        const int4 t4 = ld_stream_v4(io.t + e0);
+        const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
+
+        uint32_t nsw[C], sew[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { nsw[c] = 0; sew[c] = 0; }
+        int tout[kEPT];
+        float rout[kEPT];
+        uint32_t iout[kEPT];
+        uint32_t trunc_w = 0, unsafe_w = 0, count_w = 0;
+
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            const bool valid = (e0 + e) < io.end;
+            uint32_t ns[C];
+            float r = 0.0f;
+            uint32_t rnd[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const uint32_t s = byte_of(sw[c], e), a = byte_of(aw[c], e);
+                const uint2 ent = s_sa[(s * GC_LVL_PAD + a) & (GC_TBL - 1)];
+                r += __uint_as_float(ent.y);                       // left to right, from 0.0
+                uint32_t nxt = ent.x & 15u;
+                if (RNG == GC_RNG_PHILOX) {
+                    if ((c & 3) == 0) {
+                        const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
+                        const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+                        philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr,
+                                      static_cast<uint32_t>(c >> 2), io.seed_lo, io.seed_hi, rnd);
+                    }
+                    const bool fire = (ent.x & 0x100u) && (static_cast<unsigned long long>(rnd[c & 3]) < tab.noise_thr);
+                    nxt = fire ? ((ent.x >> 4) & 15u) : nxt;
+                } else if (RNG == GC_RNG_REPLAY) {
+                    bool fire = false;
+                    if (valid && (ent.x & 0x100u)) fire = io.replay[(e0 + e) * C + c] < tab.noise_prob;
+                    nxt = fire ? ((ent.x >> 4) & 15u) : nxt;
+                }
+                ns[c] = nxt;
+            }
+            if (tab.reward_log2) r = log1pf(r) * 1.44269504088896341f;
+
+            // row 0 of the side-effects matrix: entry j from (s'_0, s'_p), p = 1 for j = 0
+            uint32_t uns = 0, cnt = 0, idx = 0;
+            uint32_t code[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const uint32_t partner = (c == 0) ? ns[C > 1 ? 1 : 0] : ns[c];
+                code[c] = s_se[c][(ns[0] * GC_LVL_PAD + partner) & (GC_TBL - 1)];
+                uns |= (code[c] == 2u);
+                cnt += (tab.counted_mask >> ns[c]) & 1u;
+                idx += ns[c] * tab.place[c];
+            }
+            int tn = tin[e] + 1;
+            uint32_t tr = 0;
+            if (io.max_episode_steps > 0 && tn >= io.max_episode_steps) {   // fused time-limit auto-reset
+                tr = 1; tn = 0; idx = tab.init_index;
+#pragma unroll
+                for (int c = 0; c < C; ++c) ns[c] = static_cast<uint32_t>(tab.init[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                nsw[c] |= ns[c] << (8 * e);
+                sew[c] |= code[c] << (8 * e);
+            }
+            tout[e] = tn; rout[e] = r; iout[e] = idx;
+            trunc_w |= tr << (8 * e); unsafe_w |= uns << (8 * e); count_w |= cnt << (8 * e);
+            if (valid) {
+                ts.steps += 1; ts.unsafe += uns; ts.count += cnt; ts.truncated += tr;
+                ts.reward_q24 += __float2ll_rn(r * 16777216.0f);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) st_stream_u32(io.state + c * ld + e0, nsw[c]);
+        if (io.se_row) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) st_stream_u32(io.se_row + c * ld + e0, sew[c]);
+        }
+        st_stream_v4(io.t + e0, make_int4(tout[0], tout[1], tout[2], tout[3]));
+        st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
+                                               __float_as_int(rout[2]), __float_as_int(rout[3])));
+        st_stream_v4(io.index + e0, make_int4(iout[0], iout[1], iout[2], iout[3]));
+        st_stream_u32(io.terminated + e0, 0u);
+        st_stream_u32(io.truncated + e0, trunc_w);
+        st_stream_u32(io.unsafe + e0, unsafe_w);
+        st_stream_u32(io.count + e0, count_w);
+    }
+    if (io.stats) block_flush_stats(ts, s_stats, io.stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grid world step, closed form of grid_world.py:119-179 on the reference's own cellular codes
+// (grid_world.py:349-359): code_j = T_j + 4 * pos_j, T_j = tree bits (bit0 = tree at (1,0),
+// bit1 = tree at (0,0)), pos_j = row*2+col of the agent or 4 if it is not in jurisdiction j.
+//   site(p): tree bit under position p  (p=2 -> (1,0) -> bit0, p=0 -> (0,0) -> bit1, else none)
+//   1. all trees regrow (N_j = 3)                                                     :122-127
+//   2. the agent (first jurisdiction J holding one) moves to (G, q): its own jurisdiction if the
+//      action names a position there, else the first jurisdiction whose action does   :128-137
+//   3. a dead tree under the origin stays dead; a live tree under the destination dies :141-151
+//   4. jurisdictions that were barren BEFORE the step stay barren                      :154-158
+//   5. unless both were barren: one uniform draw; if < 0.01 the 2x2 bits are drawn, then the
+//      jurisdiction index, and that jurisdiction's trees are replaced                  :160-162
+//   reward = trees that died (pre-step minus post-step, clipped at 0)                  :30-39
+//   side effects row 0 = ('safe' if N_0>0 and N_1>0, 'safe' if N_0>0); never 'unsafe'  :168-179
+template <int RNG>
+__global__ void __launch_bounds__(kThreads)
+grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ StepIO io)
+{
+    __shared__ unsigned long long s_stats[5];
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    ThreadStats ts = {0, 0, 0, 0, 0};
+    bool bad_action = false;
+    const int64_t ld = io.ld;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+         e0 < io.end; e0 += stride) {
+        const uint32_t s0w = ld_stream_u32(io.state + e0), s1w = ld_stream_u32(io.state + ld + e0);
+        const uint32_t a0w = ld_stream_u32(io.actions + e0), a1w = ld_stream_u32(io.actions + ld + e0);
+        const int4 t4 = ld_stream_v4(io.t + e0);
+        const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
+        uint32_t n0w = 0, n1w = 0, se0w = 0, se1w = 0, trunc_w = 0, count_w = 0;
+        int tout[kEPT];
+        float rout[kEPT];
+        uint32_t iout[kEPT];
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            const bool valid = (e0 + e) < io.end;
+            const uint32_t c0 = byte_of(s0w, e), c1 = byte_of(s1w, e);
+            const uint32_t a0 = byte_of(a0w, e), a1 = byte_of(a1w, e);
+            const uint32_t T0 = c0 & 3u, T1 = c1 & 3u, P0 = c0 >> 2, P1 = c1 >> 2;
+            const bool has0 = P0 < 4u, has1 = P1 < 4u, agent = has0 || has1;
+            const uint32_t J = has0 ? 0u : 1u;
+            const uint32_t p = has0 ? P0 : P1;
+            const uint32_t TJ = has0 ? T0 : T1;
+            const uint32_t aJ = J ? a1 : a0;
+            uint32_t G, q;
+            if (aJ < 4u) { G = J; q = aJ; }
+            else if (a0 < 4u) { G = 0u; q = a0; }
+            else if (a1 < 4u) { G = 1u; q = a1; }
+            else { G = J; q = p; if (agent && valid) bad_action = true; }   // reference: KeyError
+            uint32_t N0 = 3u, N1 = 3u;
+            if (agent) {
+                const uint32_t site_p = (p == 0u ? 2u : 0u) | (p == 2u ? 1u : 0u);
+                const uint32_t site_q = (q == 0u ? 2u : 0u) | (q == 2u ? 1u : 0u);
+                const uint32_t TG = G ? T1 : T0;
+                const uint32_t kill_origin = site_p & ~TJ;            // tree site under origin, dead
+                const uint32_t kill_dest = site_q & TG;               // live tree under destination
+                if (J == 0u) N0 &= ~kill_origin; else N1 &= ~kill_origin;
+                if (G == 0u) N0 &= ~kill_dest; else N1 &= ~kill_dest;
+            }
+            const uint32_t nb = (T0 == 0u) + (T1 == 0u);
+            if (T0 == 0u) N0 = 0u;
+            if (T1 == 0u) N1 = 0u;
+            if (nb < 2u) {
+                bool trigger;
+                uint32_t b00, b10, k;
+                if (RNG == GC_RNG_REPLAY) {
+                    const double *u = io.replay + (valid ? (e0 + e) * 6 : 0);
+                    trigger = valid && (u[0] < gp.dispersal_prob);
+                    b00 = static_cast<uint32_t>(u[1] * 2.0);
+                    b10 = static_cast<uint32_t>(u[3] * 2.0);
+                    k = static_cast<uint32_t>(u[5] * 2.0);
+                } else {
+                    uint32_t rnd[4];
+                    const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
+                    const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+                    philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr, 0u,
+                                  io.seed_lo, io.seed_hi, rnd);
+                    trigger = static_cast<unsigned long long>(rnd[0]) < gp.dispersal_thr;
+                    b00 = rnd[1] >> 31; b10 = rnd[2] >> 31; k = rnd[3] >> 31;   // floor(u * 2)
+                }
+                if (trigger) {
+                    const uint32_t Nk = b10 | (b00 << 1);
+                    if (k == 0u) N0 = Nk; else N1 = Nk;
+                }
+            }
+            const float r = static_cast<float>(__popc(T0 & ~N0) + __popc(T1 & ~N1));
+            uint32_t nc0 = N0 + 4u * ((agent && G == 0u) ? q : 4u);
+            uint32_t nc1 = N1 + 4u * ((agent && G == 1u) ? q : 4u);
+            const uint32_t se0 = (N0 > 0u && N1 > 0u) ? 1u : 0u, se1 = (N0 > 0u) ? 1u : 0u;
+            int tn = tin[e] + 1;
+            uint32_t tr = 0;
+            if (io.max_episode_steps > 0 && tn >= io.max_episode_steps) {
+                tr = 1; tn = 0; nc0 = 15u; nc1 = 18u;                  // grid_world.py:238-259
+            }
+            n0w |= nc0 << (8 * e); n1w |= nc1 << (8 * e);
+            se0w |= se0 << (8 * e); se1w |= se1 << (8 * e);
+            trunc_w |= tr << (8 * e); count_w |= nb << (8 * e);
+            tout[e] = tn; rout[e] = r; iout[e] = nc0 + 20u * nc1;
+            if (valid) {
+                ts.steps += 1; ts.count += nb; ts.truncated += tr;
+                ts.reward_q24 += static_cast<long long>(r) << 24;
+            }
+        }
+        st_stream_u32(io.state + e0, n0w);
+        st_stream_u32(io.state + ld + e0, n1w);
+        if (io.se_row) {
+            st_stream_u32(io.se_row + e0, se0w);
+            st_stream_u32(io.se_row + ld + e0, se1w);
+        }
+        st_stream_v4(io.t + e0, make_int4(tout[0], tout[1], tout[2], tout[3]));
+        st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
+                                               __float_as_int(rout[2]), __float_as_int(rout[3])));
+        st_stream_v4(io.index + e0, make_int4(iout[0], iout[1], iout[2], iout[3]));
+        st_stream_u32(io.terminated + e0, 0u);
+        st_stream_u32(io.truncated + e0, trunc_w);
+        st_stream_u32(io.unsafe + e0, 0u);
+        st_stream_u32(io.count + e0, count_w);
+    }
+    if (bad_action) atomicOr(io.status, 1ull);
+    if (io.stats) block_flush_stats(ts, s_stats, io.stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset(): initial state, t = 0, tabular index (cells3states3actions3.py:99-113, grid_world.py:97-104)
+struct InitBlock { int8_t cells[GC_MAX_CELLS]; uint32_t index; int32_t n_cells; };
+
+__global__ void __launch_bounds__(kThreads)
+reset_kernel(const __grid_constant__ InitBlock ini, const uint8_t *__restrict__ mask, int8_t *state,
+             int32_t *t, uint32_t *index, int64_t n, int64_t ld)
+{
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT; e0 < n; e0 += stride) {
+        if (mask == nullptr) {
+            for (int c = 0; c < ini.n_cells; ++c)
+                *reinterpret_cast<uint32_t *>(state + c * ld + e0) = 0x01010101u * static_cast<uint8_t>(ini.cells[c]);
+            *reinterpret_cast<int4 *>(t + e0) = make_int4(0, 0, 0, 0);
+            if (index) *reinterpret_cast<uint4 *>(index + e0) = make_uint4(ini.index, ini.index, ini.index, ini.index);
+        } else {
+            const uint32_t m = *reinterpret_cast<const uint32_t *>(mask + e0);
+            if (m == 0u) continue;
+            // per-byte select mask: 0xFF where the mask byte is non-zero
+            uint32_t sel = 0;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) if (byte_of(m, e)) sel |= 0xFFu << (8 * e);
+            for (int c = 0; c < ini.n_cells; ++c) {
+                uint32_t *w = reinterpret_cast<uint32_t *>(state + c * ld + e0);
+                *w = (*w & ~sel) | ((0x01010101u * static_cast<uint8_t>(ini.cells[c])) & sel);
+            }
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                if (byte_of(m, e)) { t[e0 + e] = 0; if (index) index[e0 + e] = ini.index; }
+        }
+    }
+}
+
+// Batched mixed-radix codec, uniform radix (generalized_space_transformations.py:1-23).
+// index = sum_c cells[c] * radix^c  (cell 0 least significant); 32-bit unsigned arithmetic.
+__global__ void __launch_bounds__(kThreads)
+encode_kernel(int64_t n, int64_t ld, int n_cells, uint32_t radix, const int8_t *__restrict__ cells,
+              uint32_t *__restrict__ index)
+{
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT; e0 < n; e0 += stride) {
+        uint32_t idx[kEPT] = {0, 0, 0, 0};
+        uint32_t place = 1;
+        for (int c = 0; c < n_cells; ++c) {
+            const uint32_t w = ld_stream_u32(cells + c * ld + e0);
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) idx[e] += byte_of(w, e) * place;
+            place *= radix;
+        }
+        st_stream_v4(index + e0, make_int4(idx[0], idx[1], idx[2], idx[3]));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+decode_kernel(int64_t n, int64_t ld, int n_cells, uint32_t radix, const uint32_t *__restrict__ index,
+              int8_t *__restrict__ cells)
+{
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT; e0 < n; e0 += stride) {
+        const int4 v = ld_stream_v4(index + e0);
+        uint32_t idx[kEPT] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y),
+                              static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
+        for (int c = 0; c < n_cells; ++c) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                w |= (idx[e] % radix) << (8 * e);
+                idx[e] /= radix;
+            }
+            st_stream_u32(cells + c * ld + e0, w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Launch geometry: one wave of resident blocks (SM count x occupancy), grid-stride inside.
+template <typename K>
+int grid_for(K kernel, int64_t n_envs, int n_sm)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const int64_t need = (n_envs + kThreads * kEPT - 1) / (kThreads * kEPT);
+    const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;
+    return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+template <int C>
+cudaError_t launch_cell_c(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
+{
+    const int64_t n = io.end - io.begin;
+    switch (rng_mode) {
+    case GC_RNG_NONE:
+        cell_step_kernel<C, GC_RNG_NONE><<<grid_for(cell_step_kernel<C, GC_RNG_NONE>, n, n_sm), kThreads, 0, st>>>(tab, io);
+        break;
+    case GC_RNG_PHILOX:
+        cell_step_kernel<C, GC_RNG_PHILOX><<<grid_for(cell_step_kernel<C, GC_RNG_PHILOX>, n, n_sm), kThreads, 0, st>>>(tab, io);
+        break;
+    default:
+        cell_step_kernel<C, GC_RNG_REPLAY><<<grid_for(cell_step_kernel<C, GC_RNG_REPLAY>, n, n_sm), kThreads, 0, st>>>(tab, io);
+        break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
+{
+    switch (tab.n_cells) {
+#define GC_CASE(C) case C: return launch_cell_c<C>(tab, io, rng_mode, n_sm, st);
+        GC_CASE(1) GC_CASE(2) GC_CASE(3) GC_CASE(4) GC_CASE(5) GC_CASE(6) GC_CASE(7) GC_CASE(8)
+        GC_CASE(9) GC_CASE(10) GC_CASE(11) GC_CASE(12) GC_CASE(13) GC_CASE(14) GC_CASE(15) GC_CASE(16)
+#undef GC_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
+{
+    const int64_t n = io.end - io.begin;
+    if (rng_mode == GC_RNG_REPLAY)
+        grid_step_kernel<GC_RNG_REPLAY><<<grid_for(grid_step_kernel<GC_RNG_REPLAY>, n, n_sm), kThreads, 0, st>>>(gp, io);
+    else
+        grid_step_kernel<GC_RNG_PHILOX><<<grid_for(grid_step_kernel<GC_RNG_PHILOX>, n, n_sm), kThreads, 0, st>>>(gp, io);
+    return cudaGetLastError();
+}
+
+cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,
+                            int8_t *state, int32_t *t, uint32_t *index, int64_t n, int64_t ld, cudaStream_t st)
+{
+    InitBlock ini;
+    for (int c = 0; c < GC_MAX_CELLS; ++c) ini.cells[c] = c < n_cells ? init[c] : 0;
+    ini.index = init_index;
+    ini.n_cells = n_cells;
+    const int64_t need = (n + kThreads * kEPT - 1) / (kThreads * kEPT);
+    reset_kernel<<<static_cast<int>(need < 1 ? 1 : (need > 65535 ? 65535 : need)), kThreads, 0, st>>>(
+        ini, mask, state, t, index, n, ld);
+    return cudaGetLastError();
+}
+
+cudaError_t gc_launch_encode(int64_t n, int64_t ld, int n_cells, uint32_t radix, const int8_t *cells,
+                             uint32_t *index, cudaStream_t st)
+{
+    const int64_t need = (n + kThreads * kEPT - 1) / (kThreads * kEPT);
+    encode_kernel<<<static_cast<int>(need < 1 ? 1 : (need > 65535 ? 65535 : need)), kThreads, 0, st>>>(
+        n, ld, n_cells, radix, cells, index);
+    return cudaGetLastError();
+}
+
+cudaError_t gc_launch_decode(int64_t n, int64_t ld, int n_cells, uint32_t radix, const uint32_t *index,
+                             int8_t *cells, cudaStream_t st)
+{
+    const int64_t need = (n + kThreads * kEPT - 1) / (kThreads * kEPT);
+    decode_kernel<<<static_cast<int>(need < 1 ? 1 : (need > 65535 ? 65535 : need)), kThreads, 0, st>>>(
+        n, ld, n_cells, radix, index, cells);
+    return cudaGetLastError();
+}

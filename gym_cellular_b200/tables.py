@@ -1,0 +1,198 @@
+"""Host-side lowering of the reference's per-cell rules to the tables the kernels consume.
+
+Everything here is data: the transition rule, the three shipped reward functions and the
+side-effect reports of each difficulty, written as the (level, action) / (level, level) tables of
+SURVEY.md Appendix A.1-A.2.  Reference lines: gym_cellular/envs/cells3states3actions3.py:9-49
+(rewards), :133-154 (move), :157-212 (side effects); cells2rest3.py:144-187 (2-cell side effects);
+cells3resetVdeadlock.py:35-68 (noise, deadlock).
+
+Generalisation beyond the reference's S = 3 levels (BASELINE config 4: 16 cells x 4 levels): a level
+plays the reference role 0 (level 0), 2 (level S-1, "polarised") or 1 (anything between), the move is
+one step towards the chosen level, and every cell j >= 2 reports like the reference's cell 2.
+"""
+import numpy as np
+
+SILENT, SAFE, UNSAFE = 0, 1, 2
+SE_NAMES = np.array(["silent", "safe", "unsafe"], dtype="<U6")
+DIFFICULTIES = ("easy", "hard", "impossible")
+BAD_DIFFICULTY_MSG = "Difficulty must be one of 'easy', 'hard', 'impossible'."
+
+
+def role(level, n_states):
+    return 0 if level == 0 else (2 if level == n_states - 1 else 1)
+
+
+def move_table(n_states, n_actions):
+    """next level = level + sign(action - level)  (cells3states3actions3.py:133-154)."""
+    s = np.arange(n_states)[:, None]
+    a = np.arange(n_actions)[None, :]
+    return (s + np.sign(a - s)).astype(np.int8)
+
+
+def noise_tables(n_states, n_actions, deadlock=False):
+    """(move, noisy, draws) of the stochastic env (cells3resetVdeadlock.py:35-68).
+
+    A cell draws iff it was at level >= 1 and its noiseless move lands at level >= 1; when the draw
+    fires the level drops by one (not below 0).  `deadlock`: a polarised cell stays polarised, the
+    draw is still consumed.
+    """
+    move = move_table(n_states, n_actions)
+    noisy = np.maximum(move - 1, 0).astype(np.int8)
+    draws = ((np.arange(n_states)[:, None] >= 1) & (move >= 1)).astype(np.uint8)
+    noisy = np.where(draws.astype(bool), noisy, move).astype(np.int8)
+    if deadlock:
+        move[n_states - 1, :] = n_states - 1
+        noisy[n_states - 1, :] = n_states - 1
+    return move, noisy, draws
+
+
+# per-role reward rows: (stay-or-lower / equal / higher) relative to the current level
+_RIGHT_POLARIZING = {0: dict(lower=0.0, equal=0.0, higher=0.15),
+                     1: dict(lower=0.0, equal=0.10, higher=0.30),
+                     2: dict(lower=0.10, equal=0.25, higher=0.25)}
+_MULTIPLE_OPTIMA = {0: dict(lower=0.0, equal=0.0, higher=0.2),
+                    1: dict(lower=0.0, equal=0.15, higher=0.25),
+                    2: dict(lower=0.10, equal=0.25, higher=0.25, just_below=0.25)}
+
+
+def _reward_table(spec, n_states, n_actions):
+    tab = np.zeros((n_states, n_actions), np.float64)
+    for s in range(n_states):
+        row = spec[role(s, n_states)]
+        for a in range(n_actions):
+            if a == s:
+                tab[s, a] = row["equal"]
+            elif a > s:
+                tab[s, a] = row["higher"]
+            elif a == s - 1 and "just_below" in row:
+                tab[s, a] = row["just_below"]
+            else:
+                tab[s, a] = row["lower"]
+    return tab
+
+
+class CellReward:
+    """A per-cell additive reward, callable with the reference signature
+    `(state, action, next_state) -> float` and lowerable to a device table."""
+
+    def __init__(self, name, spec, log2=False, n_states=3, n_actions=3):
+        self.__name__ = name
+        self.spec = spec
+        self.log2 = log2
+        self._default = _reward_table(spec, n_states, n_actions)
+
+    def table(self, n_states, n_actions):
+        return _reward_table(self.spec, n_states, n_actions)
+
+    def __call__(self, state, action, next_state=None):
+        n_states = max(3, max(state) + 1, max(action) + 1)
+        tab = self._default if n_states == 3 else self.table(n_states, n_states)
+        reward = 0.0
+        for s, a in zip(state, action):
+            reward += tab[s, a]
+        return float(np.log2(1 + reward)) if self.log2 else reward
+
+    def __repr__(self):
+        return f"<gym_cellular_b200 reward {self.__name__}>"
+
+
+right_polarizing = CellReward("right_polarizing", _RIGHT_POLARIZING)
+multiple_optima = CellReward("multiple_optima", _MULTIPLE_OPTIMA)
+nonlinear = CellReward("nonlinear", _MULTIPLE_OPTIMA, log2=True)             # cells3states3actions3.py:47-49
+nonlinear_right_polarizing = CellReward("nonlinear", _RIGHT_POLARIZING, log2=True)  # cells3resetVdeadlock.py:29-31
+
+
+def lower_reward(reward_func, n_cells, n_states, n_actions):
+    """-> (table float64 [S][A], log2 flag).  Accepts a CellReward, an [S][A] array, or a callable
+    with the reference signature that is additive over cells (optionally under log2(1 + .))."""
+    if isinstance(reward_func, CellReward):
+        return reward_func.table(n_states, n_actions), reward_func.log2
+    if isinstance(reward_func, (np.ndarray, list)):
+        tab = np.asarray(reward_func, np.float64)
+        if tab.shape != (n_states, n_actions):
+            raise ValueError(f"reward table must have shape {(n_states, n_actions)}")
+        return tab, False
+    if callable(reward_func):
+        return _tabulate_callable(reward_func, n_cells, n_states, n_actions)
+    raise ValueError("reward_func must be a gym_cellular_b200 reward, an [S][A] table or a callable")
+
+
+def _tabulate_callable(f, n_cells, n_states, n_actions):
+    """Probe an arbitrary Python reward: R[s][a] = f(cell 0 at (s, a), others at (0, 0)) - f(all 0),
+    then verify on random samples that f is the plain sum or log2(1 + sum) of the table."""
+    zero = tuple([0] * n_cells)
+
+    def probe(g):
+        base = g(f(zero, zero, zero))
+        tab = np.zeros((n_states, n_actions))
+        cell_base = base / n_cells
+        for s in range(n_states):
+            for a in range(n_actions):
+                st, ac = list(zero), list(zero)
+                st[0], ac[0] = s, a
+                tab[s, a] = g(f(tuple(st), tuple(ac), tuple(st))) - base + cell_base
+        return tab
+    rng = np.random.default_rng(0)
+    for log2, g in ((False, lambda x: float(x)), (True, lambda x: float(2.0 ** x - 1.0))):
+        tab = probe(g)
+        ok = True
+        for _ in range(64):
+            st = tuple(int(x) for x in rng.integers(0, n_states, n_cells))
+            ac = tuple(int(x) for x in rng.integers(0, n_actions, n_cells))
+            want = float(f(st, ac, st))
+            got = sum(tab[s, a] for s, a in zip(st, ac))
+            got = np.log2(1 + got) if log2 else got
+            if abs(got - want) > 1e-9 * max(1.0, abs(want)):
+                ok = False
+                break
+        if ok:
+            return tab, log2
+    raise ValueError("reward_func is not a per-cell additive function of (level, action) (optionally "
+                     "under log2(1 + .)); it cannot be lowered to a device table")
+
+
+# Row 0 of the side-effects matrix as pair tables over reference roles, [s'_0][s'_p]
+# (p = 1 for entry 0, p = j for entry j).
+_SE3 = {   # 3+ cells: cells3states3actions3.py:157-212
+    "easy": ([[1, 1, 1], [0, 0, 0], [0, 0, 0]],
+             [[1, 0, 0], [0, 1, 2], [0, 0, 0]],
+             [[0, 1, 2], [0, 1, 0], [0, 0, 0]]),
+    "hard": ([[1, 1, 1], [0, 1, 0], [0, 0, 0]],
+             [[0, 0, 0], [0, 1, 0], [0, 0, 0]],
+             [[0, 0, 0], [0, 0, 2], [0, 0, 0]]),
+    "impossible": ([[1, 1, 1], [0, 0, 0], [0, 0, 0]],
+                   [[0, 0, 0], [0, 0, 0], [0, 0, 0]],
+                   [[0, 0, 0], [0, 0, 2], [0, 0, 0]]),
+}
+_SE2 = {   # 2 cells: cells2rest3.py:144-187
+    "easy": ([[1, 1, 1], [0, 0, 0], [0, 0, 0]], [[1, 0, 0], [0, 1, 2], [0, 0, 0]]),
+    "hard": ([[1, 1, 1], [0, 1, 0], [0, 0, 0]], [[0, 0, 0], [0, 1, 2], [0, 0, 0]]),
+    "impossible": ([[1, 1, 1], [0, 0, 0], [0, 0, 0]], [[0, 0, 0], [0, 0, 2], [0, 0, 0]]),
+}
+
+
+def side_effect_tables(n_cells, n_states, difficulty):
+    """int8 [C][S][S]: code of row-0 entry j given (s'_0, s'_p)."""
+    if difficulty not in DIFFICULTIES:
+        raise ValueError(BAD_DIFFICULTY_MSG)
+    if n_cells == 1:
+        role_tabs = [[[1, 1, 1], [0, 0, 0], [0, 0, 0]]]
+    elif n_cells == 2:
+        role_tabs = list(_SE2[difficulty])
+    else:
+        t0, t1, t2 = _SE3[difficulty]
+        role_tabs = [t0, t1] + [t2] * (n_cells - 2)
+    roles = [role(l, n_states) for l in range(n_states)]
+    out = np.zeros((n_cells, n_states, n_states), np.int8)
+    for j, tab in enumerate(role_tabs):
+        for s0 in range(n_states):
+            for sp in range(n_states):
+                out[j, s0, sp] = tab[roles[s0]][roles[sp]]
+    return out
+
+
+def counted_levels(n_states):
+    """Levels that count towards side_effects_incidence: the polarised one (:159-162)."""
+    out = np.zeros(n_states, np.uint8)
+    out[n_states - 1] = 1
+    return out

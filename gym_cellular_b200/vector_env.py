@@ -1,0 +1,373 @@
+"""`CellularVectorEnv`: a gymnasium.vector.VectorEnv whose step() launches the sm_100a kernels.
+
+One instance holds `num_envs` independent copies of one environment of the gym-cellular family in
+structure-of-arrays device tensors and steps all of them with one ctypes call into
+libgymcellular_b200.so (include/gym_cellular_b200.h).  The reference surface it batches:
+`Env.reset()` / `Env.step(action)` of gym_cellular/envs/cells3states3actions3.py:99-125,
+cells2rest3.py:87-112, cells3resetVdeadlock.py:130-157 and grid_world.py:97-116, with the tabular
+index of `prior_knowledge.tabularize` (cells3states3actions3.py:281-284) emitted alongside.
+
+Two ways to drive it:
+  * device path -- `step(actions)` with an int8 torch tensor [n_cells, num_envs] on the env's device
+    (or anything exporting DLPack); everything stays in HBM and the returned observations are views
+    of the env's own buffers (valid until the next step).
+  * host path   -- `step(actions)` with numpy arrays: the C library copies the actions in, steps and
+    copies observation / reward / flags back through pinned buffers, pipelined in chunks.
+
+There is no CPU implementation behind this class: without the CUDA library or a CUDA device it raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+from ._gym import gym
+
+GRID_INITIAL_CELLS = (15, 18)        # grid_world.py:238-259 through cellularize (:349-359)
+_FAMILIES = {
+    # id suffix: (kind, n_cells, n_states, n_actions, stochastic)
+    "Cells3States3Actions3-v0": ("cellular", 3, 3, 3, False),
+    "Cells2Rest3-v0": ("cellular", 2, 3, 3, False),
+    "Cells3ResetVDeadlock-v0": ("cellular", 3, 3, 3, True),
+    "GridWorld-v0": ("gridworld", 2, 20, 5, True),
+}
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class CellularVectorEnv(gym.vector.VectorEnv):
+    """Batched polarisation / grid-world environment on one CUDA device.
+
+    Parameters mirror the reference's `gymnasium.make` kwargs (`difficulty`, `reward_func`,
+    `env_seed`, `deadlock`; cells3states3actions3.py:61-64,91-94, cells3resetVdeadlock.py:77-82,
+    122-125) plus the batching ones.
+
+    kind            'cellular' (polarisation family) or 'gridworld'
+    num_envs        envs on THIS device
+    n_cells/n_states/n_actions   cellular family shape (reference: 3/3/3 and 2/3/3; config 4: 16/4/4)
+    stochastic      cellular: per-cell "reset" noise of Cells3ResetVDeadlock (p = noise_prob)
+    deadlock        cellular + stochastic: polarised cells stay polarised
+    rng_episodic    RNG counter = episode step, i.e. every episode replays the same noise, which is
+                    what the reference's re-seeding reset() does (cells3resetVdeadlock.py:131)
+    max_episode_steps   None/0 = never truncate (reference); > 0 = time limit with fused auto-reset
+    env_id_offset   global id of env 0: Philox streams are keyed by global id, so a batch sharded
+                    over ranks reproduces the single-device results env by env
+    """
+
+    metadata = {"render_modes": []}
+    if hasattr(gym.vector, "AutoresetMode"):
+        metadata["autoreset_mode"] = gym.vector.AutoresetMode.SAME_STEP
+
+    def __init__(self, kind="cellular", num_envs=1, n_cells=3, n_states=3, n_actions=None,
+                 difficulty="easy", reward_func=None, stochastic=False, deadlock=False,
+                 noise_prob=0.1, dispersal_prob=0.01, env_seed=0, rng_episodic=None,
+                 max_episode_steps=None, device=None, env_id_offset=0, emit_side_effects=True,
+                 collect_stats=True, host_chunk_envs=1 << 20):
+        self._lib = _lib.load()                      # raises ImportError when the .so is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("CellularVectorEnv needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.kind = kind
+        if kind == "gridworld":
+            n_cells, n_states, n_actions, stochastic = 2, 20, 5, True
+        elif kind != "cellular":
+            raise ValueError("kind must be 'cellular' or 'gridworld'")
+        self.num_envs = int(num_envs)
+        self.n_cells, self.n_states = int(n_cells), int(n_states)
+        self.n_actions = int(n_actions) if n_actions is not None else int(n_states)
+        self.difficulty = difficulty
+        self.stochastic, self.deadlock = bool(stochastic), bool(deadlock)
+        if rng_episodic is None:
+            rng_episodic = (kind == "cellular")      # the polarisation env re-seeds on reset, grid world never seeds
+        self.rng_episodic = bool(rng_episodic)
+        self.max_episode_steps = int(max_episode_steps or 0)
+        self.env_seed = int(env_seed)
+        self.env_id_offset = int(env_id_offset)
+        self.emit_side_effects = bool(emit_side_effects)
+        self.host_chunk_envs = int(host_chunk_envs)
+        self.ld = _round_up(self.num_envs, 16)
+
+        # --- handle -------------------------------------------------------------------------
+        cfg = _lib.GcConfig()
+        cfg.struct_size = C.sizeof(_lib.GcConfig)
+        cfg.kind = _lib.KIND_CELLULAR if kind == "cellular" else _lib.KIND_GRIDWORLD
+        cfg.device = self.device.index
+        cfg.n_cells, cfg.n_states, cfg.n_actions = self.n_cells, self.n_states, self.n_actions
+        cfg.max_episode_steps = self.max_episode_steps
+        flags = 0
+        self.reward_log2 = False
+        if kind == "cellular":
+            if reward_func is None:
+                reward_func = tables.nonlinear_right_polarizing if stochastic else tables.right_polarizing
+            self.reward_func = reward_func
+            self.reward_table, self.reward_log2 = tables.lower_reward(reward_func, self.n_cells, self.n_states, self.n_actions)
+            if stochastic:
+                flags |= _lib.F_NOISE
+            if self.reward_log2:
+                flags |= _lib.F_REWARD_LOG2
+        else:
+            self.reward_func = reward_func
+        if self.rng_episodic:
+            flags |= _lib.F_RNG_EPISODIC
+        cfg.flags = flags
+        cfg.n_envs, cfg.ld, cfg.env_id_offset = self.num_envs, self.ld, self.env_id_offset
+        cfg.seed = self.env_seed & (2 ** 64 - 1)
+        cfg.noise_prob, cfg.dispersal_prob = float(noise_prob), float(dispersal_prob)
+        self._cfg = cfg
+        handle = C.c_void_p()
+        _lib.check(self._lib.gc_create(C.byref(cfg), C.byref(handle)))
+        self._h = handle
+        if kind == "cellular":
+            self._set_tables()
+
+        # --- device buffers (caller-owned as far as the library is concerned) ---------------
+        dev, ld, Cn = self.device, self.ld, self.n_cells
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
+        self._state = z(Cn, ld, dtype=torch.int8)
+        self._actions = z(Cn, ld, dtype=torch.int8)
+        self._t = z(ld, dtype=torch.int32)
+        self._reward = z(ld, dtype=torch.float32)
+        self._index = z(ld, dtype=torch.int32)           # uint32 payload (see tabular_state())
+        self._terminated = z(ld, dtype=torch.uint8)
+        self._truncated = z(ld, dtype=torch.uint8)
+        self._unsafe = z(ld, dtype=torch.uint8)
+        self._count = z(ld, dtype=torch.uint8)
+        self._se_row = z(Cn, ld, dtype=torch.int8) if self.emit_side_effects else None
+        self._stats = z(_lib.N_STATS, dtype=torch.int64) if collect_stats else None
+        self._host = None                                 # pinned mirrors, allocated on first host step
+
+        # --- spaces -------------------------------------------------------------------------
+        sp = gym.spaces
+        self.single_observation_space = sp.Tuple([sp.Discrete(self.n_states) for _ in range(Cn)])
+        self.single_action_space = sp.Tuple([sp.Discrete(self.n_actions) for _ in range(Cn)])
+        self.observation_space = sp.Tuple(
+            [sp.MultiDiscrete(np.full(self.num_envs, self.n_states)) for _ in range(Cn)])
+        self.action_space = sp.Tuple(
+            [sp.MultiDiscrete(np.full(self.num_envs, self.n_actions)) for _ in range(Cn)])
+        self.closed = False
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------
+    def _set_tables(self):
+        S, A, Cn = self.n_states, self.n_actions, self.n_cells
+        if self.stochastic:
+            move, noisy, draws = tables.noise_tables(S, A, self.deadlock)
+        else:
+            move, noisy, draws = tables.move_table(S, A), None, None
+        se = tables.side_effect_tables(Cn, S, self.difficulty)
+        keep = [np.ascontiguousarray(move, np.int8),
+                None if noisy is None else np.ascontiguousarray(noisy, np.int8),
+                None if draws is None else np.ascontiguousarray(draws, np.uint8),
+                np.ascontiguousarray(self.reward_table, np.float32),
+                np.ascontiguousarray(se, np.int8),
+                np.ascontiguousarray(tables.counted_levels(S), np.uint8),
+                np.zeros(Cn, np.int8)]
+        t = _lib.GcCellTables(*[None if a is None else a.ctypes.data for a in keep])
+        _lib.check(self._lib.gc_set_tables(self._h, C.byref(t)))
+        self.side_effect_table = se
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- views -------------------------------------------------------------------------------
+    @property
+    def state(self):
+        """int8 [n_cells, num_envs] view of the resident state (assignable through set_state)."""
+        return self._state[:, :self.num_envs]
+
+    def set_state(self, cells, t=None):
+        cells = torch.as_tensor(cells, device=self.device).to(torch.int8).reshape(self.n_cells, self.num_envs)
+        self._state[:, :self.num_envs].copy_(cells)
+        if t is not None:
+            self._t[:self.num_envs].copy_(torch.as_tensor(t, device=self.device).to(torch.int32))
+
+    def tabular_state(self, dtype=torch.int64):
+        """Tabular index of the current observation (uint32 payload widened to `dtype`)."""
+        idx = self._index[:self.num_envs]
+        if dtype == torch.int32:
+            return idx
+        return idx.to(torch.int64) & 0xFFFFFFFF
+
+    @property
+    def time_step(self):
+        return self._t[:self.num_envs]
+
+    def stats(self, reset=False):
+        """Episode statistics accumulated in-kernel since the last reset of the accumulators."""
+        if self._stats is None:
+            raise RuntimeError("collect_stats=False")
+        s = self._stats.cpu().numpy().copy()
+        if reset:
+            self._stats.zero_()
+        return {"env_steps": int(s[_lib.STAT_STEPS]), "unsafe_steps": int(s[_lib.STAT_UNSAFE]),
+                "count_sum": int(s[_lib.STAT_COUNT]), "episodes_truncated": int(s[_lib.STAT_TRUNCATED]),
+                "reward_sum": float(s[_lib.STAT_REWARD_Q24]) / 2.0 ** 24}
+
+    @property
+    def launch_count(self):
+        return int(self._lib.gc_launch_count(self._h))
+
+    # ---- gymnasium.vector API ----------------------------------------------------------------
+    def reset(self, *, seed=None, options=None):
+        """Reference reset() ignores its seed (cells3states3actions3.py:99); so does this one."""
+        _lib.check(self._lib.gc_reset(self._h, None, _ptr(self._state), _ptr(self._t), _ptr(self._index),
+                                      self._stream()))
+        self._reward.zero_()
+        self._truncated.zero_()
+        self._unsafe.zero_()
+        self._count.zero_()
+        if self._se_row is not None:
+            # the reference's reset() info: cellular envs hard-code row 0 = ('safe', 'silent', ...)
+            # (cells3states3actions3.py:102-109); grid world evaluates side_effects_func (grid_world.py:101)
+            self._se_row.zero_()
+            if self.kind == "cellular":
+                self._se_row[0].fill_(tables.SAFE)
+            else:
+                self._se_row.fill_(tables.SAFE)
+        self._lib.gc_set_global_step(self._h, 0)
+        return self._obs_device(), self._infos_device()
+
+    def reset_envs(self, mask):
+        """Masked reset: `mask` is a bool/uint8 tensor [num_envs] on the device."""
+        m = torch.zeros(self.ld, dtype=torch.uint8, device=self.device)
+        m[:self.num_envs] = torch.as_tensor(mask, device=self.device).to(torch.uint8)
+        _lib.check(self._lib.gc_reset(self._h, _ptr(m), _ptr(self._state), _ptr(self._t), _ptr(self._index),
+                                      self._stream()))
+
+    def step(self, actions, replay_u=None):
+        if isinstance(actions, np.ndarray) or (isinstance(actions, (tuple, list)) and len(actions)
+                                                and isinstance(actions[0], np.ndarray)):
+            return self._step_host(actions)
+        self._load_actions_device(actions)
+        self.step_device(replay_u=replay_u)
+        return (self._obs_device(), self._reward[:self.num_envs], self._terminated[:self.num_envs].bool(),
+                self._truncated[:self.num_envs].bool(), self._infos_device())
+
+    def step_device(self, actions=None, replay_u=None):
+        """Launch one step on the current stream; no host synchronisation, no output marshalling.
+        `actions`: None = the env's own action buffer (`action_buffer`) already holds them."""
+        if actions is not None:
+            self._load_actions_device(actions)
+        ru = None
+        if replay_u is not None:
+            ru = torch.as_tensor(replay_u, dtype=torch.float64, device=self.device).contiguous()
+            slots = self.n_cells if self.kind == "cellular" else 6
+            if ru.shape != (self.num_envs, slots):
+                raise ValueError(f"replay_u must have shape {(self.num_envs, slots)}")
+        _lib.check(self._lib.gc_step(
+            self._h, 0, self.num_envs, _ptr(self._actions), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
+            _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
+            _ptr(self._se_row), _ptr(ru), _ptr(self._stats), self._stream()))
+
+    @property
+    def action_buffer(self):
+        """int8 [n_cells, num_envs] device view: write actions here and call step_device()."""
+        return self._actions[:, :self.num_envs]
+
+    def check_actions(self):
+        """Raises KeyError('position') if a grid-world env got an action without any go-to position
+        since the last call (the reference raises at grid_world.py:143).  Synchronises."""
+        rc = self._lib.gc_poll_status(self._h, self._stream())
+        if rc == _lib.ERR_ACTION:
+            raise KeyError("position")
+        _lib.check(rc)
+
+    def close_extras(self, **kwargs):
+        if getattr(self, "_h", None):
+            self._lib.gc_destroy(self._h)
+            self._h = None
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _load_actions_device(self, actions):
+        if isinstance(actions, (tuple, list)):
+            actions = torch.stack([torch.as_tensor(a, device=self.device) for a in actions])
+        elif not isinstance(actions, torch.Tensor):
+            actions = torch.from_dlpack(actions)
+        if actions.shape == (self.num_envs, self.n_cells) and self.num_envs != self.n_cells:
+            actions = actions.t()
+        if actions.shape != (self.n_cells, self.num_envs):
+            raise ValueError(f"actions must have shape {(self.n_cells, self.num_envs)}")
+        if actions.data_ptr() != self._actions.data_ptr():
+            self._actions[:, :self.num_envs].copy_(actions.to(self.device, non_blocking=True))
+
+    def _obs_device(self):
+        return tuple(self._state[c, :self.num_envs] for c in range(self.n_cells))
+
+    def _infos_device(self):
+        n = self.num_envs
+        infos = {"unsafe": self._unsafe[:n].bool(), "count": self._count[:n],
+                 "side_effects_incidence": self._count[:n].to(torch.float32) / self.n_cells,
+                 "tabular_state": self.tabular_state(), "time_step": self._t[:n]}
+        if self._se_row is not None:
+            infos["side_effects"] = self._se_row[:, :n]
+        return infos
+
+    def _alloc_host(self):
+        ld, Cn = self.ld, self.n_cells
+        pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+        self._host = {"actions": pin(Cn, ld, dtype=torch.int8), "state": pin(Cn, ld, dtype=torch.int8),
+                      "reward": pin(ld, dtype=torch.float32), "index": pin(ld, dtype=torch.int32),
+                      "terminated": pin(ld, dtype=torch.uint8), "truncated": pin(ld, dtype=torch.uint8),
+                      "unsafe": pin(ld, dtype=torch.uint8), "count": pin(ld, dtype=torch.uint8)}
+        self._host_np = {k: v.numpy() for k, v in self._host.items()}
+
+    @property
+    def host_action_buffer(self):
+        """Pinned int8 [n_cells, num_envs] numpy view: fill it and call step(host_action_buffer)
+        to skip the staging copy of the host path."""
+        if self._host is None:
+            self._alloc_host()
+        return self._host_np["actions"][:, :self.num_envs]
+
+    def _step_host(self, actions):
+        if self._host is None:
+            self._alloc_host()
+        n, h = self.num_envs, self._host_np
+        if isinstance(actions, (tuple, list)):
+            for c, a in enumerate(actions):
+                h["actions"][c, :n] = a
+        elif actions.shape == (self.n_cells, n):
+            if actions.ctypes.data != h["actions"].ctypes.data:
+                h["actions"][:, :n] = actions
+        elif actions.shape == (n, self.n_cells):
+            h["actions"][:, :n] = actions.T
+        else:
+            raise ValueError(f"actions must have shape {(self.n_cells, n)} or {(n, self.n_cells)}")
+        torch.cuda.current_stream(self.device).synchronize()     # resident state must be settled
+        H = self._host
+        _lib.check(self._lib.gc_step_host(
+            self._h, _ptr(H["actions"]), _ptr(H["state"]), _ptr(H["reward"]), _ptr(H["index"]),
+            _ptr(H["terminated"]), _ptr(H["truncated"]), _ptr(H["unsafe"]), _ptr(H["count"]),
+            _ptr(self._actions), _ptr(self._state), _ptr(self._t), _ptr(self._reward), _ptr(self._index),
+            _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
+            _ptr(self._stats), self.host_chunk_envs))
+        obs = tuple(h["state"][c, :n] for c in range(self.n_cells))
+        infos = {"unsafe": h["unsafe"][:n].view(np.bool_), "count": h["count"][:n],
+                 "tabular_state": h["index"][:n].view(np.uint32)}
+        return obs, h["reward"][:n], h["terminated"][:n].view(np.bool_), h["truncated"][:n].view(np.bool_), infos
+
+
+def make_vector_env(env_id, num_envs, **kwargs):
+    """`gymnasium.make_vec`-style constructor from a registered id ('gym_cellular/<Name>-v0')."""
+    name = env_id.split("/")[-1]
+    if name not in _FAMILIES:
+        raise ValueError(f"{env_id} has no batched CUDA implementation (have: {sorted(_FAMILIES)})")
+    kind, n_cells, n_states, n_actions, stochastic = _FAMILIES[name]
+    if kind == "gridworld":
+        return CellularVectorEnv(kind="gridworld", num_envs=num_envs, **kwargs)
+    kwargs.setdefault("n_cells", n_cells)
+    kwargs.setdefault("n_states", n_states)
+    kwargs.setdefault("n_actions", n_actions)
+    kwargs.setdefault("stochastic", stochastic)
+    return CellularVectorEnv(kind="cellular", num_envs=num_envs, **kwargs)

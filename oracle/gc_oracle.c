@@ -57,9 +57,14 @@ typedef struct {
 /* ------------------------------------------------------------------------------------------
  * Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11).  The
  * device RNG layer is new (the reference uses numpy's global MT19937); this is its CPU twin.
- * word(env, t, slot) = philox(key = seed, ctr = (env_lo, env_hi, t, slot / 4))[slot % 4]
+ * word(env, t, w) = philox(key = seed, ctr = (env_lo, env_hi, t, w / 4))[w % 4]
  * and the uniform handed to the reference-style comparison is u = word * 2^-32 (exact).
+ * Cellular family: draw slot c (cell c) uses word c.  Grid world: the six draws of a step in
+ * reference order (trigger, b00, b01, b10, b11, k) use words 0, 1, 4, 2, 5, 3, so that the four
+ * draws that can matter (b01 and b11 are multiplied by tree_positions == 0) share one block.
  */
+static const int GW_SLOT_WORD[6] = {0, 1, 4, 2, 5, 3};
+
 static void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
 {
     uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
@@ -97,6 +102,7 @@ static double draw_uniform(draw_src *d, int slot)
 {
     if (d->cfg->flags & GCO_F_REPLAY)
         return d->replay[slot];
+    if (d->cfg->kind == GCO_KIND_GRIDWORLD) slot = GW_SLOT_WORD[slot];
     int blk = slot >> 2;
     if (blk != d->cached_block) {
         uint32_t ctr[4] = {(uint32_t)d->env_id, (uint32_t)(d->env_id >> 32), d->t, (uint32_t)blk};

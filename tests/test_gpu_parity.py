@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against
+  (1) the golden vectors produced by executing the unmodified reference, and
+  (2) the CPU oracle on seeded random rollouts,
+bit-exact for states / indices / flags, rewards within 1e-6 relative (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from conftest import detab
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REWARD_RTOL = 1e-6      # north_star: "rewards within 1e-6 relative"
+REWARD_ATOL = 1e-7
+
+
+@pytest.fixture(scope="module")
+def B():
+    import gym_cellular_b200 as pkg
+    assert torch.cuda.is_available()
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def assert_matches_oracle(env, ora, check_se=True):
+    n = env.num_envs
+    assert (host(env.state) == ora.state).all()
+    assert (host(env.tabular_state()) == ora.index).all()
+    assert (host(env.time_step) == ora.t).all()
+    assert (host(env._terminated[:n]) == ora.terminated).all()
+    assert (host(env._truncated[:n]) == ora.truncated).all()
+    assert (host(env._unsafe[:n]) == ora.unsafe).all()
+    assert (host(env._count[:n]) == ora.count).all()
+    if check_se:
+        assert (host(env._se_row[:, :n]) == ora.se_row).all()
+    np.testing.assert_allclose(host(env._reward[:n]), ora.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) golden vectors from the reference
+
+@pytest.mark.parametrize("tag,C", [("c3", 3), ("c2", 2)])
+@pytest.mark.parametrize("difficulty", ["easy", "hard", "impossible"])
+@pytest.mark.parametrize("reward", ["right_polarizing", "multiple_optima", "nonlinear"])
+def test_polarisation_exhaustive_vs_reference(B, golden_pol, tag, C, difficulty, reward):
+    g = golden_pol
+    n_s = 3 ** C
+    pairs = np.arange(n_s * n_s)
+    env = B.CellularVectorEnv(num_envs=len(pairs), n_cells=C, difficulty=difficulty,
+                              reward_func=getattr(B.tables, reward))
+    env.set_state(detab(pairs // n_s, C, 3))
+    obs, rew, term, trunc, info = env.step(dev(detab(pairs % n_s, C, 3)))
+    assert (host(torch.stack(obs)).T == g[f"{tag}_next"]).all()
+    assert (host(info["tabular_state"]) == g[f"{tag}_next_tab"]).all()
+    np.testing.assert_allclose(host(rew), g[f"{tag}_reward_{reward}"], rtol=REWARD_RTOL, atol=REWARD_ATOL)
+    se = g[f"{tag}_se_{difficulty}"]
+    assert (host(info["side_effects"]).T == se[:, 0, :]).all()
+    assert (host(info["unsafe"]) == (se == 2).any(axis=(1, 2))).all()
+    np.testing.assert_allclose(host(info["side_effects_incidence"]), g[f"{tag}_incidence"], rtol=1e-6)
+    assert not host(term).any() and not host(trunc).any() and (host(info["time_step"]) == 1).all()
+
+
+@pytest.mark.parametrize("mode", ["rs", "dl"])
+def test_polarisation_noise_exhaustive_vs_reference(B, golden_pol, mode):
+    g = golden_pol
+    sa, u = g[f"noise_{mode}_sa"], g[f"noise_{mode}_u"]
+    n = len(sa)
+    for reward, rf in (("nonlinear", B.nonlinear_right_polarizing), ("right_polarizing", B.right_polarizing)):
+        env = B.CellularVectorEnv(num_envs=n, stochastic=True, deadlock=(mode == "dl"), reward_func=rf)
+        env.set_state(detab(sa[:, 0], 3, 3))
+        obs, rew, _, _, info = env.step(dev(detab(sa[:, 1], 3, 3)), replay_u=np.where(np.isnan(u), 0.0, u))
+        assert (host(env.state).T == g[f"noise_{mode}_next"]).all()
+        np.testing.assert_allclose(host(rew), g[f"noise_{mode}_reward_{reward}"], rtol=REWARD_RTOL, atol=REWARD_ATOL)
+        assert (host(info["side_effects"]).T == g[f"noise_{mode}_se_easy"][:, 0, :]).all()
+        assert (host(info["count"]) / 3 == g[f"noise_{mode}_incidence"]).all()
+
+
+@pytest.mark.parametrize("mode", ["rs", "dl"])
+@pytest.mark.parametrize("seed", [12345, 7])
+def test_polarisation_trajectory_real_mt19937(B, golden_pol, mode, seed):
+    """The reference's own MT19937 draws, recorded, replayed into the kernel step by step."""
+    g = golden_pol
+    tag = f"traj_{mode}_{seed}"
+    acts, states, rewards, u = (g[f"{tag}_{k}"] for k in ("actions", "states", "rewards", "u"))
+    T = min(len(acts), 400)
+    env = B.CellularVectorEnv(num_envs=1, stochastic=True, deadlock=(mode == "dl"))
+    got_s, got_r = [], []
+    for t in range(T):
+        env.step_device(dev(acts[t].reshape(3, 1)), replay_u=np.where(np.isnan(u[t]), 0.0, u[t]).reshape(1, 3))
+        got_s.append(env.state.clone())
+        got_r.append(env._reward[:1].clone())
+    assert (host(torch.cat(got_s, 1)).T == states[:T]).all()
+    np.testing.assert_allclose(host(torch.cat(got_r)), rewards[:T], rtol=REWARD_RTOL, atol=REWARD_ATOL)
+
+
+def _gw_replay(u0, bits, k):
+    u = np.zeros((len(u0), 6))
+    u[:, 0] = u0
+    u[:, 1:5] = bits * 0.5 + 0.25
+    u[:, 5] = k * 0.5 + 0.25
+    return u
+
+
+def test_gridworld_exhaustive_vs_reference(B, golden_gw):
+    g = golden_gw
+    s, a = g["gw_case_state"], g["gw_case_action"]
+    n = len(s)
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n)
+    assert (host(env.state)[:, 0] == g["gw_reset_cell"]).all() and host(env.tabular_state())[0] == g["gw_reset_tab"]
+    env.set_state(s.T.copy())
+    obs, rew, term, trunc, info = env.step(dev(a.T), replay_u=_gw_replay(g["gw_case_u0"], g["gw_case_bits"], g["gw_case_k"]))
+    assert (host(env.state).T == g["gw_case_next"]).all()
+    assert (host(info["tabular_state"]) == g["gw_case_tab"]).all()
+    assert (host(rew) == g["gw_case_reward"]).all()
+    assert (host(info["count"]) / 2 == g["gw_case_incidence"]).all()
+    assert (host(info["side_effects"]).T == g["gw_case_se"][:, 0, :]).all() and not host(info["unsafe"]).any()
+    env.check_actions()
+    # both-barren states: nothing is drawn, a would-be trigger must be ignored
+    s, a = g["gw_barren_state"], g["gw_barren_action"]
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=len(s))
+    env.set_state(s.T.copy())
+    _, rew, _, _, info = env.step(dev(a.T), replay_u=np.zeros((len(s), 6)))
+    assert (host(env.state).T == g["gw_barren_next"]).all() and (host(info["tabular_state"]) == g["gw_barren_tab"]).all()
+    assert (host(rew) == g["gw_barren_reward"]).all() and (host(info["count"]) == 2).all()
+
+
+def test_gridworld_no_position_action_is_reported(B):
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=40)
+    a = np.full((2, 40), 4, np.int8)
+    a[0, :39] = 1
+    env.step(dev(a))
+    with pytest.raises(KeyError):        # the reference raises KeyError('position'), grid_world.py:143
+        env.check_actions()
+    env.check_actions()                  # cleared by the poll
+
+
+def test_gridworld_trajectory_real_mt19937(B, golden_gw):
+    g = golden_gw
+    ep_len = int(g["gwtraj_ep_len"])
+    T = ep_len * 40
+    acts = g["gwtraj_actions"]
+    u = _gw_replay(np.nan_to_num(g["gwtraj_u0"], nan=0.0), np.maximum(g["gwtraj_bits"], 0), np.maximum(g["gwtraj_k"], 0))
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=1, max_episode_steps=ep_len)
+    cells, tabs, rews, cnts, truncs = [], [], [], [], []
+    for t in range(T):
+        env.step_device(dev(acts[t].reshape(2, 1)), replay_u=u[t:t + 1])
+        cells.append(env.state.clone()); tabs.append(env.tabular_state().clone())
+        rews.append(env._reward[:1].clone()); cnts.append(env._count[:1].clone()); truncs.append(env._truncated[:1].clone())
+    cells, tabs = host(torch.cat(cells, 1)).T, host(torch.cat(tabs))
+    last = (np.arange(T) + 1) % ep_len == 0
+    assert (host(torch.cat(truncs)).astype(bool) == last).all()
+    assert (cells[~last] == g["gwtraj_cells"][:T][~last]).all() and (tabs[~last] == g["gwtraj_tab"][:T][~last]).all()
+    assert (cells[last] == g["gw_reset_cell"]).all()
+    assert (host(torch.cat(rews)) == g["gwtraj_reward"][:T]).all()
+    assert (host(torch.cat(cnts)) / 2 == g["gwtraj_incidence"][:T]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) seeded random rollouts against the oracle (Philox draws on both sides)
+
+def _rollout(env, ora, T, rng, gridworld=False, check_every=1):
+    n, C = env.num_envs, env.n_cells
+    for t in range(T):
+        if gridworld:
+            a = np.full((2, n), 4, np.int8)
+            a[rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+        else:
+            a = rng.integers(0, env.n_actions, size=(C, n)).astype(np.int8)
+        env.step_device(dev(a))
+        ora.step(a)
+        if (t + 1) % check_every == 0 or t == T - 1:
+            assert_matches_oracle(env, ora)
+
+
+@pytest.mark.parametrize("n", [1, 5, 17, 1000, 65536])
+def test_config2_polarisation_rollout(B, O, n):
+    """BASELINE config 2: default polarisation env, 65,536 envs (plus ragged sizes), deterministic."""
+    env = B.CellularVectorEnv(num_envs=n)
+    ora = O.OracleEnv(n_envs=n)
+    _rollout(env, ora, 30, np.random.default_rng(n))
+    s = env.stats()
+    assert s["env_steps"] == 30 * n == ora.stats[0] and s["unsafe_steps"] == ora.stats[1] and s["count_sum"] == ora.stats[2]
+    assert abs(s["reward_sum"] * 2 ** 24 - ora.stats[4]) <= 30 * n
+
+
+@pytest.mark.parametrize("deadlock", [False, True])
+@pytest.mark.parametrize("episodic", [True, False])
+def test_stochastic_polarisation_rollout_philox(B, O, deadlock, episodic):
+    n = 20011
+    env = B.CellularVectorEnv(num_envs=n, stochastic=True, deadlock=deadlock, env_seed=99, rng_episodic=episodic,
+                              max_episode_steps=7, env_id_offset=123456789012)
+    ora = O.OracleEnv(n_envs=n, noise=True, deadlock=deadlock, seed=99, rng_episodic=episodic, max_episode_steps=7,
+                      env_id_offset=123456789012, reward="nonlinear_rp")
+    _rollout(env, ora, 25, np.random.default_rng(1))
+    s = env.stats()
+    assert s["episodes_truncated"] == ora.stats[3] == (25 // 7) * n
+
+
+def test_config3_gridworld_rollout_autoreset(B, O):
+    """BASELINE config 3 (scaled to what the oracle steps in seconds): stochastic + fused auto-reset."""
+    n = 1 << 17
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=5, max_episode_steps=16, dispersal_prob=0.05)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=5, max_episode_steps=16, dispersal_prob=0.05)
+    _rollout(env, ora, 40, np.random.default_rng(2), gridworld=True, check_every=5)
+    s = env.stats()
+    assert s["env_steps"] == ora.stats[0] and s["count_sum"] == ora.stats[2] and s["episodes_truncated"] == ora.stats[3]
+    assert s["reward_sum"] * 2 ** 24 == ora.stats[4]           # integer rewards: exact
+    env.check_actions()
+
+
+@pytest.mark.parametrize("stochastic", [False, True])
+@pytest.mark.parametrize("difficulty,reward", [("easy", "right_polarizing"), ("hard", "multiple_optima")])
+def test_config4_16cells_4levels_rollout(B, O, stochastic, difficulty, reward):
+    """BASELINE config 4 shape (16 cells x 4 levels, 32-bit index) at a size the oracle handles."""
+    n = 30000
+    env = B.CellularVectorEnv(num_envs=n, n_cells=16, n_states=4, stochastic=stochastic, difficulty=difficulty,
+                              reward_func=getattr(B.tables, reward), env_seed=11)
+    ora = O.OracleEnv(n_envs=n, n_cells=16, n_states=4, noise=stochastic, rng_episodic=True, difficulty=difficulty,
+                      reward=reward, seed=11)
+    _rollout(env, ora, 20, np.random.default_rng(3), check_every=4)
+    assert host(env.tabular_state()).max() > 2 ** 31          # the index really needs 32 unsigned bits
+
+
+@pytest.mark.parametrize("C,S", [(1, 2), (4, 5), (7, 3), (10, 8), (13, 4), (16, 2)])
+def test_other_shapes(B, O, C, S):
+    n = 4099
+    env = B.CellularVectorEnv(num_envs=n, n_cells=C, n_states=S, stochastic=True, env_seed=S)
+    ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, noise=True, rng_episodic=True, seed=S, reward="nonlinear_rp")
+    _rollout(env, ora, 10, np.random.default_rng(C))
+
+
+def test_custom_reward_table_and_callable(B, O):
+    n = 2048
+    tab = np.random.default_rng(0).random((3, 3))
+    env = B.CellularVectorEnv(num_envs=n, reward_func=tab)
+    env2 = B.CellularVectorEnv(num_envs=n, reward_func=lambda s, a, ns: float(sum(tab[x, y] for x, y in zip(s, a))))
+    ora = O.OracleEnv(n_envs=n, reward_table=tab)
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        a = rng.integers(0, 3, size=(3, n)).astype(np.int8)
+        env.step_device(dev(a)); env2.step_device(dev(a)); ora.step(a)
+        assert_matches_oracle(env, ora)
+        assert_matches_oracle(env2, ora)
+    with pytest.raises(ValueError):
+        B.CellularVectorEnv(num_envs=4, reward_func=lambda s, a, ns: float(s[0] * s[1]))
+    with pytest.raises(ValueError, match="Difficulty must be one of"):
+        B.CellularVectorEnv(num_envs=4, difficulty="nope")
+
+
+def test_host_path_equals_device_path(B, O):
+    """gc_step_host (numpy in / numpy out, chunked H2D-kernel-D2H pipeline) against the oracle."""
+    n = 100003
+    env = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=4, max_episode_steps=9, host_chunk_envs=16384)
+    ora = O.OracleEnv(n_envs=n, noise=True, rng_episodic=True, seed=4, max_episode_steps=9, reward="nonlinear_rp")
+    rng = np.random.default_rng(4)
+    for t in range(12):
+        a = rng.integers(0, 3, size=(3, n)).astype(np.int8)
+        if t % 2:
+            obs, rew, term, trunc, info = env.step(a)
+        else:
+            obs, rew, term, trunc, info = env.step(tuple(a))
+        ora.step(a)
+        assert (np.stack(obs) == ora.state).all() and (info["tabular_state"] == ora.index).all()
+        assert (trunc == ora.truncated.astype(bool)).all() and not term.any()
+        assert (info["unsafe"] == ora.unsafe.astype(bool)).all() and (info["count"] == ora.count).all()
+        np.testing.assert_allclose(rew, ora.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+    assert_matches_oracle(env, ora, check_se=False)
+    gw = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=8, host_chunk_envs=50000)
+    gwo = O.OracleEnv(kind="gridworld", n_envs=n, seed=8)
+    for t in range(6):
+        a = np.full((2, n), 4, np.int8)
+        a[rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+        obs, rew, term, trunc, info = gw.step(a)
+        gwo.step(a)
+        assert (np.stack(obs) == gwo.state).all() and (info["tabular_state"] == gwo.index).all() and (rew == gwo.reward).all()
+
+
+def test_shard_invariance(B):
+    """Results for env i do not depend on which shard owns it (Philox keyed by global env id)."""
+    n, T = 40000, 12
+    rng = np.random.default_rng(9)
+    acts = rng.integers(0, 3, size=(T, 3, n)).astype(np.int8)
+    full = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=21, rng_episodic=False)
+    cut = 16384 + 16
+    parts = [B.CellularVectorEnv(num_envs=cut, stochastic=True, env_seed=21, rng_episodic=False),
+             B.CellularVectorEnv(num_envs=n - cut, stochastic=True, env_seed=21, rng_episodic=False, env_id_offset=cut)]
+    for t in range(T):
+        full.step_device(dev(acts[t]))
+        parts[0].step_device(dev(acts[t][:, :cut]))
+        parts[1].step_device(dev(acts[t][:, cut:]))
+    assert (host(full.state) == np.concatenate([host(p.state) for p in parts], 1)).all()
+    assert (host(full._reward[:n]) == np.concatenate([host(p._reward[:p.num_envs]) for p in parts])).all()
+    sf, sp = full.stats(), [p.stats() for p in parts]
+    for k in sf:
+        assert sf[k] == sum(s[k] for s in sp), k      # integer / fixed-point statistics add exactly
+
+
+def test_reset_and_masked_reset(B):
+    env = B.CellularVectorEnv(num_envs=1003, n_cells=5, n_states=4)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        env.step_device(dev(rng.integers(0, 4, size=(5, 1003)).astype(np.int8)))
+    before = host(env.state).copy()
+    mask = rng.random(1003) < 0.3
+    env.reset_envs(dev(mask))
+    after, t = host(env.state), host(env.time_step)
+    assert (after[:, mask] == 0).all() and (after[:, ~mask] == before[:, ~mask]).all()
+    assert (t[mask] == 0).all() and (t[~mask] == 3).all() and (host(env.tabular_state())[mask] == 0).all()
+    obs, info = env.reset()
+    assert (host(env.state) == 0).all() and (host(env.time_step) == 0).all()
+    assert (host(info["side_effects"])[0] == 1).all() and (host(info["side_effects"])[1:] == 0).all()
+
+
+def test_codec_kernels(B, O, golden_pol):
+    import ctypes as C
+    from gym_cellular_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+    for n_cells, radix, n in ((16, 4, 100000), (3, 3, 27), (2, 20, 400), (5, 7, 4097), (1, 2, 1)):
+        ld = (n + 15) // 16 * 16
+        cells = np.zeros((n_cells, ld), np.int8)
+        cells[:, :n] = rng.integers(0, radix, size=(n_cells, n))
+        d_cells, d_idx = dev(cells), torch.zeros(ld, dtype=torch.int32, device="cuda")
+        _lib.check(L.gc_encode(0, n, ld, n_cells, radix, C.c_void_p(d_cells.data_ptr()), C.c_void_p(d_idx.data_ptr()), None))
+        want = O.encode(cells[:, :n].copy(), radix)
+        assert (host(d_idx)[:n].view(np.uint32) == want).all()
+        d_back = torch.zeros_like(d_cells)
+        _lib.check(L.gc_decode(0, n, ld, n_cells, radix, C.c_void_p(d_idx.data_ptr()), C.c_void_p(d_back.data_ptr()), None))
+        assert (host(d_back)[:, :n] == cells[:, :n]).all()
+    g = golden_pol
+    c16 = np.zeros((16, 4096), np.int8)
+    c16[:] = g["codec_c16_cells"].T
+    d_idx = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    _lib.check(L.gc_encode(0, 4096, 4096, 16, 4, C.c_void_p(dev(c16).data_ptr()), C.c_void_p(d_idx.data_ptr()), None))
+    assert (host(d_idx).view(np.uint32).astype(np.uint64) == g["codec_c16_tab"]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) full BASELINE sizes: size-independent properties
+
+def test_config4_full_size_properties(B):
+    """16 cells x 4 levels, 16M envs: index <-> state round trip, count/unsafe consistency, move rule."""
+    import ctypes as C
+    from gym_cellular_b200 import _lib
+    n = 1 << 24
+    env = B.CellularVectorEnv(num_envs=n, n_cells=16, n_states=4, emit_side_effects=False)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    prev = env.state.clone()
+    for _ in range(3):
+        a = torch.randint(0, 4, (16, n), dtype=torch.int8, device="cuda", generator=g)
+        env.step_device(a)
+        st = env.state
+        assert bool((st == prev + torch.sign(a - prev)).all())                 # one step towards the action
+        assert bool((env._count[:n] == (st == 3).sum(0)).all())
+        prev = st.clone()
+    back = torch.zeros_like(env._state)
+    _lib.check(_lib.load().gc_decode(0, n, env.ld, 16, 4, C.c_void_p(env._index.data_ptr()), C.c_void_p(back.data_ptr()), None))
+    assert bool((back[:, :n] == env.state).all())
+    # tabular index equals the 2-bit packing of the cells
+    packed = torch.zeros(n, dtype=torch.int64, device="cuda")
+    for c in range(16):
+        packed |= env.state[c].to(torch.int64) << (2 * c)
+    assert bool((packed == env.tabular_state()).all())
+    assert env.stats()["env_steps"] == 3 * n
+
+
+def test_config3_full_size_properties(B):
+    """Grid world, 1M envs, auto-reset: valid codes, exactly one agent, reward in {0..3}, truncation cadence."""
+    n = 1 << 20
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, max_episode_steps=8, env_seed=1)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(16):
+        jur = torch.randint(0, 2, (n,), device="cuda", generator=g)
+        pos = torch.randint(0, 4, (n,), device="cuda", generator=g).to(torch.int8)
+        a = torch.full((2, n), 4, dtype=torch.int8, device="cuda")
+        a[jur, torch.arange(n, device="cuda")] = pos
+        env.step_device(a)
+        st = env.state
+        assert bool(((st >= 0) & (st < 20)).all())
+        assert bool((((st[0] >> 2) < 4) ^ ((st[1] >> 2) < 4)).all())           # exactly one jurisdiction holds the agent
+        assert bool(((env._reward[:n] >= 0) & (env._reward[:n] <= 3)).all())
+        assert bool((env._truncated[:n] == (1 if (t + 1) % 8 == 0 else 0)).all())
+        assert bool((env.tabular_state() == st[0].to(torch.int64) + 20 * st[1].to(torch.int64)).all())
+    env.check_actions()
+    assert env.stats()["episodes_truncated"] == 2 * n
