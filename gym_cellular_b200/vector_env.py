@@ -334,11 +334,14 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if self._host is None:
             self._alloc_host()
         n, h = self.num_envs, self._host_np
+        h_actions_ptr = _ptr(self._host["actions"])
         if isinstance(actions, (tuple, list)):
             for c, a in enumerate(actions):
                 h["actions"][c, :n] = a
         elif actions.shape == (self.n_cells, n):
-            if actions.ctypes.data != h["actions"].ctypes.data:
+            if actions.dtype == np.int8 and actions.flags.c_contiguous and n == self.ld:
+                h_actions_ptr = C.c_void_p(actions.ctypes.data)      # caller's buffer (pinned or not), no staging copy
+            elif actions.ctypes.data != h["actions"].ctypes.data:
                 h["actions"][:, :n] = actions
         elif actions.shape == (n, self.n_cells):
             h["actions"][:, :n] = actions.T
@@ -347,7 +350,7 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         torch.cuda.current_stream(self.device).synchronize()     # resident state must be settled
         H = self._host
         _lib.check(self._lib.gc_step_host(
-            self._h, _ptr(H["actions"]), _ptr(H["state"]), _ptr(H["reward"]), _ptr(H["index"]),
+            self._h, h_actions_ptr, _ptr(H["state"]), _ptr(H["reward"]), _ptr(H["index"]),
             _ptr(H["terminated"]), _ptr(H["truncated"]), _ptr(H["unsafe"]), _ptr(H["count"]),
             _ptr(self._actions), _ptr(self._state), _ptr(self._t), _ptr(self._reward), _ptr(self._index),
             _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
