@@ -50,6 +50,8 @@ struct gc_env {
     int64_t global_step;
     int64_t launches;
     unsigned long long *d_status;
+    uint2 *d_pair_lut;            // fast-path table (GC_PAIR_LUT_ENTRIES), device memory owned by the handle
+    bool fast_ok;
     cudaStream_t hstream[kHostStreams];
     cudaEvent_t hevent[kHostStreams];
     bool host_ready;
@@ -102,7 +104,10 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
     cudaError_t e;
     if (env->cfg.kind == GC_KIND_CELLULAR) {
         const int mode = io.replay ? GC_RNG_REPLAY : ((env->cfg.flags & GC_F_NOISE) ? GC_RNG_PHILOX : GC_RNG_NONE);
-        e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);
+        if (mode == GC_RNG_NONE && env->fast_ok)
+            e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, env->n_sm, st);
+        else
+            e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);
     } else {
         e = gc_launch_grid_step(env->grid, io, io.replay ? GC_RNG_REPLAY : GC_RNG_PHILOX, env->n_sm, st);
     }
@@ -174,6 +179,7 @@ int gc_destroy(gc_env *env)
             cudaEventDestroy(env->hevent[i]);
         }
     if (env->d_status) cudaFree(env->d_status);
+    if (env->d_pair_lut) cudaFree(env->d_pair_lut);
     delete env;
     return GC_OK;
 }
@@ -221,6 +227,47 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     tab.reward_log2 = (env->cfg.flags & GC_F_REWARD_LOG2) ? 1 : 0;
     tab.noise_thr = threshold_of(env->cfg.noise_prob);
     tab.noise_prob = env->cfg.noise_prob;
+
+    // ---- fast path: pair table (see gc_cell_fast.cu) -------------------------------------------
+    env->fast_ok = !noise && S <= 4 && A <= 4;
+    for (int j = 3; j < C && env->fast_ok; ++j)
+        if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
+            env->fast_ok = false;
+    if (env->fast_ok) {
+        auto mv = [&](int s, int a) { return (s < S && a < A) ? (int)t->move[s * A + a] : 0; };
+        auto rw = [&](int s, int a) { return (s < S && a < A) ? (double)t->reward[s * A + a] : 0.0; };
+        auto se = [&](int j, int s0, int sp) { return (int)t->side_effects[((size_t)j * S + s0) * S + sp]; };
+        auto cn = [&](int n) { return t->counted[n] ? 1u : 0u; };
+        static_assert(GC_PAIR_LUT_ENTRIES == 272, "pair table layout");
+        uint2 lut[GC_PAIR_LUT_ENTRIES];
+        for (int p = 0; p < 256; ++p) {
+            const int sc = p & 3, ac = (p >> 2) & 3, sd = (p >> 4) & 3, ad = (p >> 6) & 3;
+            const int nc = mv(sc, ac), nd = mv(sd, ad);
+            const uint32_t uns01 = (C >= 2 && (se(0, nc, nd) == 2 || se(1, nc, nd) == 2)) ? 1u : 0u;
+            lut[p].x = (cn(nc) + cn(nd)) | (((1u << nc) | (1u << nd)) << 8) | (uns01 << 12) |
+                       ((uint32_t)nc << 16) | ((uint32_t)nd << 24);
+            lut[p].y = 0;
+            const float f = (float)(rw(sc, ac) + rw(sd, ad));
+            std::memcpy(&lut[p].y, &f, sizeof(f));
+        }
+        for (int p = 0; p < 16; ++p) {
+            const int s = p & 3, a = (p >> 2) & 3, n = mv(s, a);
+            const uint32_t uns0 = (C == 1 && se(0, n, n) == 2) ? 1u : 0u;
+            lut[256 + p].x = cn(n) | ((1u << n) << 8) | (uns0 << 12) | ((uint32_t)n << 16);
+            const float f = (float)rw(s, a);
+            std::memcpy(&lut[256 + p].y, &f, sizeof(f));
+        }
+        tab.unsafe_rows = 0;
+        if (C >= 3)
+            for (int s0 = 0; s0 < S; ++s0)
+                for (int x = 0; x < S; ++x)
+                    if (se(2, s0, x) == 2) tab.unsafe_rows |= (1u << x) << (8 * s0);
+        uint32_t p4 = 1;
+        for (int i = 0; i < 4; ++i) { tab.place4[i] = p4; p4 *= (uint32_t)S; }
+        GC_CUDA(cudaSetDevice(env->cfg.device));
+        if (!env->d_pair_lut) GC_CUDA(cudaMalloc(&env->d_pair_lut, sizeof(lut)));
+        GC_CUDA(cudaMemcpy(env->d_pair_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    }
     env->tables_set = true;
     return GC_OK;
 }

@@ -39,6 +39,8 @@ struct CellTables {
     float    reward[GC_TBL];
     uint8_t  se[GC_MAX_CELLS][GC_TBL]; // [j][s0' * GC_LVL_PAD + s'_p]
     uint32_t place[GC_MAX_CELLS];    // mixed-radix place values S^c (mod 2^32)
+    uint32_t place4[4];              // S^0..S^3: digits of four cells folded into one byte (fast path)
+    uint32_t unsafe_rows;            // byte s0': set of levels x with SE[j>=2][s0'][x] == unsafe (fast path)
     int8_t   init[GC_MAX_CELLS];
     uint32_t init_index;
     uint32_t counted_mask;           // bit l set: level l counts towards the incidence
@@ -60,6 +62,10 @@ struct LaunchGeom {
 
 cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm,
                                 cudaStream_t stream);
+// fast path (S, A <= 4, deterministic): lut = 256 pair entries + 16 single-cell entries, device memory
+#define GC_PAIR_LUT_ENTRIES (256 + 16)
+cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
+                                     cudaStream_t stream);
 cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm,
                                 cudaStream_t stream);
 cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,
