@@ -92,6 +92,10 @@ StepIO make_io(const gc_env *env, int64_t begin, int64_t count, const int8_t *ac
     io.env_id_offset = env->cfg.env_id_offset;
     io.seed_lo = static_cast<uint32_t>(env->cfg.seed);
     io.seed_hi = static_cast<uint32_t>(env->cfg.seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        io.round_key[2 * r] = io.seed_lo + static_cast<uint32_t>(r) * 0x9E3779B9u;
+        io.round_key[2 * r + 1] = io.seed_hi + static_cast<uint32_t>(r) * 0xBB67AE85u;
+    }
     io.rng_counter = static_cast<uint32_t>(env->global_step);
     io.episodic = (env->cfg.flags & GC_F_RNG_EPISODIC) ? 1 : 0;
     io.max_episode_steps = env->cfg.max_episode_steps;
@@ -104,8 +108,8 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
     cudaError_t e;
     if (env->cfg.kind == GC_KIND_CELLULAR) {
         const int mode = io.replay ? GC_RNG_REPLAY : ((env->cfg.flags & GC_F_NOISE) ? GC_RNG_PHILOX : GC_RNG_NONE);
-        if (mode == GC_RNG_NONE && env->fast_ok)
-            e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, env->n_sm, st);
+        if (env->fast_ok)
+            e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, mode, env->n_sm, st);
         else
             e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);
     } else {
@@ -157,13 +161,25 @@ int gc_create(const gc_config *cfg, gc_env **out)
     env->cfg = *cfg;
     GC_CUDA(cudaDeviceGetAttribute(&env->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     env->grid.dispersal_thr = threshold_of(cfg->dispersal_prob);
+    env->grid.dispersal_thr_nz = env->grid.dispersal_thr != 0ull;
+    env->grid.dispersal_thr_m1 = env->grid.dispersal_thr_nz ? static_cast<uint32_t>(env->grid.dispersal_thr - 1ull) : 0u;
     env->grid.dispersal_prob = cfg->dispersal_prob;
     env->tables_set = (cfg->kind == GC_KIND_GRIDWORLD);
     cudaError_t e = cudaMalloc(&env->d_status, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(env->d_status, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess && cfg->kind == GC_KIND_GRIDWORLD) {
+        static uint32_t lut[GC_GRID_LUT_ENTRIES];
+        gc_build_grid_lut(lut);
+        uint32_t *d_lut = nullptr;
+        e = cudaMalloc(&d_lut, sizeof(lut));
+        if (e == cudaSuccess) e = cudaMemcpy(d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+        env->grid.lut = d_lut;
+    }
     if (e != cudaSuccess) {
+        if (env->d_status) cudaFree(env->d_status);
+        if (env->grid.lut) cudaFree(const_cast<uint32_t *>(env->grid.lut));
         delete env;
-        return fail(GC_ERR_CUDA, "status word allocation failed: %s", cudaGetErrorString(e));
+        return fail(GC_ERR_CUDA, "device table allocation failed: %s", cudaGetErrorString(e));
     }
     *out = env;
     return GC_OK;
@@ -180,6 +196,7 @@ int gc_destroy(gc_env *env)
         }
     if (env->d_status) cudaFree(env->d_status);
     if (env->d_pair_lut) cudaFree(env->d_pair_lut);
+    if (env->grid.lut) cudaFree(const_cast<uint32_t *>(env->grid.lut));
     delete env;
     return GC_OK;
 }
@@ -228,40 +245,17 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     tab.noise_thr = threshold_of(env->cfg.noise_prob);
     tab.noise_prob = env->cfg.noise_prob;
 
-    // ---- fast path: pair table (see gc_cell_fast.cu) -------------------------------------------
-    env->fast_ok = !noise && S <= 4 && A <= 4;
+    tab.noise_thr_nz = tab.noise_thr != 0ull;
+    tab.noise_thr_m1 = tab.noise_thr_nz ? static_cast<uint32_t>(tab.noise_thr - 1ull) : 0u;
+
+    // ---- fast path: pair table (gc_cell_fast.cu) -------------------------------------------------
+    env->fast_ok = S <= 4 && A <= 4;
     for (int j = 3; j < C && env->fast_ok; ++j)
         if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
             env->fast_ok = false;
     if (env->fast_ok) {
-        auto mv = [&](int s, int a) { return (s < S && a < A) ? (int)t->move[s * A + a] : 0; };
-        auto rw = [&](int s, int a) { return (s < S && a < A) ? (double)t->reward[s * A + a] : 0.0; };
-        auto se = [&](int j, int s0, int sp) { return (int)t->side_effects[((size_t)j * S + s0) * S + sp]; };
-        auto cn = [&](int n) { return t->counted[n] ? 1u : 0u; };
-        static_assert(GC_PAIR_LUT_ENTRIES == 272, "pair table layout");
-        uint2 lut[GC_PAIR_LUT_ENTRIES];
-        for (int p = 0; p < 256; ++p) {
-            const int sc = p & 3, ac = (p >> 2) & 3, sd = (p >> 4) & 3, ad = (p >> 6) & 3;
-            const int nc = mv(sc, ac), nd = mv(sd, ad);
-            const uint32_t uns01 = (C >= 2 && (se(0, nc, nd) == 2 || se(1, nc, nd) == 2)) ? 1u : 0u;
-            lut[p].x = (cn(nc) + cn(nd)) | (((1u << nc) | (1u << nd)) << 8) | (uns01 << 12) |
-                       ((uint32_t)nc << 16) | ((uint32_t)nd << 24);
-            lut[p].y = 0;
-            const float f = (float)(rw(sc, ac) + rw(sd, ad));
-            std::memcpy(&lut[p].y, &f, sizeof(f));
-        }
-        for (int p = 0; p < 16; ++p) {
-            const int s = p & 3, a = (p >> 2) & 3, n = mv(s, a);
-            const uint32_t uns0 = (C == 1 && se(0, n, n) == 2) ? 1u : 0u;
-            lut[256 + p].x = cn(n) | ((1u << n) << 8) | (uns0 << 12) | ((uint32_t)n << 16);
-            const float f = (float)rw(s, a);
-            std::memcpy(&lut[256 + p].y, &f, sizeof(f));
-        }
-        tab.unsafe_rows = 0;
-        if (C >= 3)
-            for (int s0 = 0; s0 < S; ++s0)
-                for (int x = 0; x < S; ++x)
-                    if (se(2, s0, x) == 2) tab.unsafe_rows |= (1u << x) << (8 * s0);
+        static uint2 lut[GC_PAIR_LUT_ENTRIES];
+        gc_build_pair_lut(t, C, S, A, noise, lut, &tab.unsafe_rows);
         uint32_t p4 = 1;
         for (int i = 0; i < 4; ++i) { tab.place4[i] = p4; p4 *= (uint32_t)S; }
         GC_CUDA(cudaSetDevice(env->cfg.device));

@@ -1,7 +1,10 @@
-// Fast path of the deterministic cellular (polarisation) step for S, A <= 4 levels.
+// Fast path of the cellular (polarisation) step for S, A <= 4 levels, deterministic or stochastic.
 //
-// Two cells at a time: the four 2-bit digits (s_c, a_c, s_d, a_d) of a cell pair form one byte that
-// indexes a 256-entry table staged in shared memory.  One 64-bit shared load returns, for the pair,
+// Two cells at a time: the four 2-bit digits (s_c, a_c, s_d, a_d) of a cell pair form one byte that,
+// together with one "the noise draw of this cell fired" bit per cell in the stochastic case
+// (cells3resetVdeadlock.py:35-61; Philox word < threshold, or a replayed uniform < p), indexes a table
+// staged in shared memory (256 entries deterministic, 1024 stochastic; built on the host by
+// gc_build_pair_lut).  One 64-bit shared load returns, for the pair,
 //   .y  the reward contribution R[s_c][a_c] + R[s_d][a_d]                (cells3states3actions3.py:9-45)
 //   .x  bits  0-4   how many of the two next levels count towards the incidence     (:159-162)
 //       bits  8-11  one-hot set of the two next levels ("presence", for the side-effect report)
@@ -24,20 +27,22 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // requested up front (memory-level parallelism), so wide envs trade occupancy for loads in flight
 constexpr int pair_min_blocks(int c) { return c > 8 ? 2 : (c > 4 ? 3 : 4); }
 
-template <int C, bool WITH_SE>
+template <int C, int RNG, bool WITH_SE>
 __global__ void __launch_bounds__(kThreads, pair_min_blocks(C))
 cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ StepIO io,
                  const uint2 *__restrict__ lut)
 {
     constexpr int NP = C / 2;
     constexpr bool ODD = (C & 1) != 0;
-    __shared__ uint2 s_pair[256];
-    __shared__ uint2 s_single[16];
+    constexpr int N_PAIR = (RNG == GC_RNG_NONE) ? 256 : GC_PAIR_LUT_PAIRS;
+    constexpr int N_SINGLE = (RNG == GC_RNG_NONE) ? 16 : 32;
+    __shared__ uint2 s_pair[N_PAIR];
+    __shared__ uint2 s_single[N_SINGLE];
     __shared__ uint8_t s_se[WITH_SE ? C : 1][GC_TBL];
     __shared__ unsigned long long s_stats[5];
 
-    for (int i = threadIdx.x; i < 256; i += kThreads) s_pair[i] = lut[i];
-    if (threadIdx.x < 16) s_single[threadIdx.x] = lut[256 + threadIdx.x];
+    for (int i = threadIdx.x; i < N_PAIR; i += kThreads) s_pair[i] = lut[i];
+    if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
     if (WITH_SE)
         for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
@@ -55,7 +60,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
             aw[c] = ld_stream_u32(io.actions + c * ld + e0) & 0x03030303u;   // keep byte lanes apart
         }
         const int4 t4 = ld_stream_v4(io.t + e0);
+        const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
         int tn[kEPT] = {t4.x + 1, t4.y + 1, t4.z + 1, t4.w + 1};
+        uint32_t rnd[kEPT][4];                                     // Philox block of the current 4 cells
         uint32_t trunc_w = 0, keep = 0xFFFFFFFFu;                 // keep: byte mask of envs NOT reset
         if (io.max_episode_steps > 0) {
 #pragma unroll
@@ -73,11 +80,30 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
             const int c = 2 * k, d = 2 * k + 1;
             const bool pair = k < NP;
             uint32_t inf[kEPT];
+            if (RNG == GC_RNG_PHILOX && (c & 3) == 0) {
+#pragma unroll
+                for (int e = 0; e < kEPT; ++e) {
+                    const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
+                    const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+                    philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr,
+                                  static_cast<uint32_t>(c >> 2), io.round_key, rnd[e]);
+                }
+            }
+            // fire(e, cell): did the noise draw of that cell fire?  (ignored by the table where the
+            // (level, action) pair consumes no draw)
+            auto fire = [&](int e, int cell) -> uint32_t {
+                if (RNG == GC_RNG_PHILOX) return (tab.noise_thr_nz && rnd[e][cell & 3] <= tab.noise_thr_m1) ? 1u : 0u;
+                if (RNG == GC_RNG_REPLAY)
+                    return ((e0 + e) < io.end && io.replay[(e0 + e) * C + cell] < tab.noise_prob) ? 1u : 0u;
+                return 0u;
+            };
             if (pair) {
                 const uint32_t pidx = (aw[d] * 4u + (sw[d] & 0x03030303u)) * 16u + aw[c] * 4u + (sw[c] & 0x03030303u);
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e) {
-                    const uint2 ent = s_pair[byte_of(pidx, e)];
+                    uint32_t ix = byte_of(pidx, e);
+                    if (RNG != GC_RNG_NONE) ix |= (fire(e, c) << 8) | (fire(e, d) << 9);
+                    const uint2 ent = s_pair[ix];
                     r[e] += __uint_as_float(ent.y);
                     inf[e] = ent.x;
                 }
@@ -85,7 +111,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                 const uint32_t sidx = aw[c] * 4u + (sw[c] & 0x03030303u);
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e) {
-                    const uint2 ent = s_single[byte_of(sidx, e) & 15u];
+                    uint32_t ix = byte_of(sidx, e) & 15u;
+                    if (RNG != GC_RNG_NONE) ix |= fire(e, c) << 4;
+                    const uint2 ent = s_single[ix];
                     r[e] += __uint_as_float(ent.y);
                     inf[e] = ent.x;
                 }
@@ -158,24 +186,35 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     if (io.stats) block_flush_stats(ts, s_stats, io.stats);
 }
 
-template <int C>
-cudaError_t launch_pair_c(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm, cudaStream_t st)
+template <int C, int RNG>
+cudaError_t launch_pair_cr(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm, cudaStream_t st)
 {
     const int64_t n = io.end - io.begin;
     if (io.se_row)
-        cell_pair_kernel<C, true><<<grid_for(cell_pair_kernel<C, true>, n, n_sm), kThreads, 0, st>>>(tab, io, lut);
+        cell_pair_kernel<C, RNG, true><<<grid_for<cell_pair_kernel<C, RNG, true>>(n, n_sm), kThreads, 0, st>>>(tab, io, lut);
     else
-        cell_pair_kernel<C, false><<<grid_for(cell_pair_kernel<C, false>, n, n_sm), kThreads, 0, st>>>(tab, io, lut);
+        cell_pair_kernel<C, RNG, false><<<grid_for<cell_pair_kernel<C, RNG, false>>(n, n_sm), kThreads, 0, st>>>(tab, io, lut);
     return cudaGetLastError();
+}
+
+template <int C>
+cudaError_t launch_pair_c(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode, int n_sm,
+                          cudaStream_t st)
+{
+    switch (rng_mode) {
+    case GC_RNG_NONE: return launch_pair_cr<C, GC_RNG_NONE>(tab, io, lut, n_sm, st);
+    case GC_RNG_PHILOX: return launch_pair_cr<C, GC_RNG_PHILOX>(tab, io, lut, n_sm, st);
+    default: return launch_pair_cr<C, GC_RNG_REPLAY>(tab, io, lut, n_sm, st);
+    }
 }
 
 }  // namespace
 
-cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
-                                     cudaStream_t st)
+cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode,
+                                     int n_sm, cudaStream_t st)
 {
     switch (tab.n_cells) {
-#define GC_CASE(C) case C: return launch_pair_c<C>(tab, io, lut, n_sm, st);
+#define GC_CASE(C) case C: return launch_pair_c<C>(tab, io, lut, rng_mode, n_sm, st);
         GC_CASE(1) GC_CASE(2) GC_CASE(3) GC_CASE(4) GC_CASE(5) GC_CASE(6) GC_CASE(7) GC_CASE(8)
         GC_CASE(9) GC_CASE(10) GC_CASE(11) GC_CASE(12) GC_CASE(13) GC_CASE(14) GC_CASE(15) GC_CASE(16)
 #undef GC_CASE

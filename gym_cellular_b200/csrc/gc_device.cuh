@@ -8,20 +8,20 @@ constexpr int kThreads = 256;
 constexpr int kEPT = 4;
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10, counter based: word w of env e at step t = philox(key=seed, ctr=(e_lo,e_hi,t,w/4))[w%4]
+// Philox4x32-10, counter based: word w of env e at step t = philox(key=seed, ctr=(e_lo,e_hi,t,w/4))[w%4].
+// rk = the ten round keys (k0 + r*W0, k1 + r*W1), warp-uniform (StepIO::round_key): a round is two
+// 32x32->64 multiplies and two three-input XORs.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+                                              const uint32_t (&rk)[20], uint32_t (&out)[4])
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
+        const unsigned long long p0 = static_cast<unsigned long long>(0xD2511F53u) * c0;
+        const unsigned long long p1 = static_cast<unsigned long long>(0xCD9E8D57u) * c2;
+        c0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk[2 * r];
+        c1 = static_cast<uint32_t>(p1);
+        c2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c3 = static_cast<uint32_t>(p0);
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
@@ -71,11 +71,13 @@ __device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigne
 
 // ---------------------------------------------------------------------------------------------
 // Launch geometry: one wave of resident blocks (SM count x occupancy), grid-stride inside.
-template <typename K>
-int grid_for(K kernel, int64_t n_envs, int n_sm)
+template <auto Kernel>
+int grid_for(int64_t n_envs, int n_sm)
 {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+    const auto kernel = Kernel;
+    static int per_sm = 0;               // one static per kernel instantiation: query the occupancy once
+    if (per_sm == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1))
         per_sm = 1;
     const int64_t need = (n_envs + kThreads * kEPT - 1) / (kThreads * kEPT);
     const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;

@@ -1,0 +1,141 @@
+// Grid-world step (gym_cellular/envs/grid_world.py:107-179) as a table lookup.
+//
+// The deterministic part of the transition -- movement, tree death, regrowth, erosion, reward and
+// the side-effect report -- is a function of (code_0, code_1, a_0, a_1) with 20*20*5*5 = 10,000
+// cases; the host tabulates it once (gc_tables.cu: gc_build_grid_lut, closed form of :119-158) and
+// each block stages the 40 KB table into shared memory.  Per env-step the kernel does one shared
+// load; the seed-dispersal event (:160-162, probability 0.01, one Philox block per env-step unless
+// both jurisdictions are barren) patches the looked-up result in-line.
+#include "gc_device.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+
+template <int RNG>
+__global__ void __launch_bounds__(kThreads, 4)
+grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ StepIO io)
+{
+    __shared__ uint32_t s_lut[GC_GRID_LUT_ENTRIES];
+    __shared__ unsigned long long s_stats[5];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (int i = threadIdx.x; i < GC_GRID_LUT_ENTRIES / 4; i += kThreads) dst[i] = src[i];
+    }
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    ThreadStats ts = {0, 0, 0, 0, 0};
+    bool bad_action = false;
+    const int64_t ld = io.ld;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+         e0 < io.end; e0 += stride) {
+        const uint32_t s0w = ld_stream_u32(io.state + e0), s1w = ld_stream_u32(io.state + ld + e0);
+        uint32_t a0w = ld_stream_u32(io.actions + e0), a1w = ld_stream_u32(io.actions + ld + e0);
+        const int4 t4 = ld_stream_v4(io.t + e0);
+        const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
+        // action codes above 4 mean "no position" like 4 (per-byte min(a, 4)); state codes are ours
+        a0w = __vminu4(a0w, 0x04040404u);
+        a1w = __vminu4(a1w, 0x04040404u);
+        const uint32_t actw = a0w + a1w * 5u;                       // a_0 + 5 a_1 <= 24 per byte
+        uint32_t ent[kEPT];
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            const uint32_t tab = byte_of(s0w, e) + 20u * byte_of(s1w, e);
+            const uint32_t ix = tab * 25u + byte_of(actw, e);
+            ent[e] = s_lut[ix < GC_GRID_LUT_ENTRIES ? ix : 0];
+        }
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            const uint32_t nb = (ent[e] >> 18) & 3u;
+            if (nb < 2u) {                                           // grid_world.py:160
+                const bool valid = (e0 + e) < io.end;
+                bool trigger;
+                uint32_t b00, b10, k;
+                if (RNG == GC_RNG_REPLAY) {
+                    const double *u = io.replay + (valid ? (e0 + e) * 6 : 0);
+                    trigger = valid && (u[0] < gp.dispersal_prob);
+                    b00 = static_cast<uint32_t>(u[1] * 2.0);
+                    b10 = static_cast<uint32_t>(u[3] * 2.0);
+                    k = static_cast<uint32_t>(u[5] * 2.0);
+                } else {
+                    uint32_t rnd[4];
+                    const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
+                    const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+                    philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr, 0u,
+                                  io.round_key, rnd);
+                    trigger = gp.dispersal_thr_nz && (rnd[0] <= gp.dispersal_thr_m1);
+                    b00 = rnd[1] >> 31; b10 = rnd[2] >> 31; k = rnd[3] >> 31;       // floor(u * 2)
+                }
+                if (trigger) {
+                    // the drawn 2x2 bits (times tree_positions) replace jurisdiction k's trees: :162
+                    const uint32_t T0 = byte_of(s0w, e) & 3u, T1 = byte_of(s1w, e) & 3u;
+                    uint32_t nc0 = ent[e] & 0xFFu, nc1 = (ent[e] >> 8) & 0xFFu;
+                    const uint32_t Nk = b10 | (b00 << 1);
+                    if (k == 0u) nc0 = (nc0 & ~3u) | Nk; else nc1 = (nc1 & ~3u) | Nk;
+                    const uint32_t N0 = nc0 & 3u, N1 = nc1 & 3u;
+                    const uint32_t rew = __popc(T0 & ~N0) + __popc(T1 & ~N1);
+                    const uint32_t se0 = (N0 > 0u && N1 > 0u) ? 1u : 0u, se1 = (N0 > 0u) ? 1u : 0u;
+                    ent[e] = nc0 | (nc1 << 8) | (rew << 16) | (nb << 18) | (se0 << 20) | (se1 << 21) |
+                             (ent[e] & (1u << 22));
+                }
+            }
+        }
+        uint32_t trunc_w = 0, count_w = 0, se0w = 0, se1w = 0;
+        int tout[kEPT];
+        float rout[kEPT];
+        uint32_t iout[kEPT];
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            const bool valid = (e0 + e) < io.end;
+            const uint32_t rew = (ent[e] >> 16) & 3u, nb = (ent[e] >> 18) & 3u;
+            int tn = tin[e] + 1;
+            uint32_t tr = 0;
+            if (valid && (ent[e] & (1u << 22))) bad_action = true;
+            if (io.max_episode_steps > 0 && tn >= io.max_episode_steps) {
+                tr = 1; tn = 0;
+                ent[e] = (ent[e] & 0xFFFF0000u) | 15u | (18u << 8);               // grid_world.py:238-259
+            }
+            tout[e] = tn; rout[e] = static_cast<float>(rew);
+            iout[e] = (ent[e] & 0xFFu) + 20u * ((ent[e] >> 8) & 0xFFu);
+            trunc_w |= tr << (8 * e); count_w |= nb << (8 * e);
+            se0w |= ((ent[e] >> 20) & 1u) << (8 * e); se1w |= ((ent[e] >> 21) & 1u) << (8 * e);
+            if (valid) {
+                ts.steps += 1; ts.count += nb; ts.truncated += tr;
+                ts.reward_q24 += static_cast<long long>(rew) << 24;
+            }
+        }
+        // SoA rows of the next state: byte 0 / byte 1 of the four entries
+        const uint32_t u = prmt(ent[0], ent[1], 0x5140), v = prmt(ent[2], ent[3], 0x5140);
+        st_stream_u32(io.state + e0, prmt(u, v, 0x5410));
+        st_stream_u32(io.state + ld + e0, prmt(u, v, 0x7632));
+        if (io.se_row) {
+            st_stream_u32(io.se_row + e0, se0w);
+            st_stream_u32(io.se_row + ld + e0, se1w);
+        }
+        st_stream_v4(io.t + e0, make_int4(tout[0], tout[1], tout[2], tout[3]));
+        st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
+                                               __float_as_int(rout[2]), __float_as_int(rout[3])));
+        st_stream_v4(io.index + e0, make_int4(iout[0], iout[1], iout[2], iout[3]));
+        st_stream_u32(io.terminated + e0, 0u);
+        st_stream_u32(io.truncated + e0, trunc_w);
+        st_stream_u32(io.unsafe + e0, 0u);                          // never 'unsafe': grid_world.py:174-175
+        st_stream_u32(io.count + e0, count_w);
+    }
+    if (bad_action) atomicOr(io.status, 1ull);
+    if (io.stats) block_flush_stats(ts, s_stats, io.stats);
+}
+
+}  // namespace
+
+cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
+{
+    const int64_t n = io.end - io.begin;
+    if (rng_mode == GC_RNG_REPLAY)
+        grid_step_kernel<GC_RNG_REPLAY><<<grid_for<grid_step_kernel<GC_RNG_REPLAY>>(n, n_sm), kThreads, 0, st>>>(gp, io);
+    else
+        grid_step_kernel<GC_RNG_PHILOX><<<grid_for<grid_step_kernel<GC_RNG_PHILOX>>(n, n_sm), kThreads, 0, st>>>(gp, io);
+    return cudaGetLastError();
+}

@@ -27,6 +27,7 @@ struct StepIO {
     int64_t ld;
     int64_t env_id_offset;
     uint32_t seed_lo, seed_hi;
+    uint32_t round_key[20];     // Philox round keys (k0_r, k1_r), r = 0..9: warp-uniform, precomputed on the host
     uint32_t rng_counter;       // global step (ignored when episodic)
     int32_t  episodic;
     int32_t  max_episode_steps;
@@ -47,13 +48,26 @@ struct CellTables {
     int32_t  n_cells, n_states, n_actions;
     int32_t  reward_log2;
     unsigned long long noise_thr;    // draw fires iff word < noise_thr  (word*2^-32 < p)
+    uint32_t noise_thr_m1;           // noise_thr - 1 (32-bit compare: fires iff thr != 0 and word <= thr - 1)
+    uint32_t noise_thr_nz;
     double   noise_prob;             // for the replay path (compares doubles like the reference)
 };
 
 struct GridParams {
     unsigned long long dispersal_thr;
+    uint32_t dispersal_thr_m1, dispersal_thr_nz;
     double dispersal_prob;
+    const uint32_t *lut;             // GC_GRID_LUT_ENTRIES transition entries, device memory (handle-owned)
 };
+
+// Grid-world transition table: entry index = (code_0 + 20 * code_1) * 25 + (a_0 + 5 * a_1)
+#define GC_GRID_LUT_ENTRIES (400 * 25)
+// entry layout: byte 0 next code_0, byte 1 next code_1, bits 16-17 reward (trees that died),
+// bits 18-19 barren jurisdictions before the step, bit 20 / 21 row-0 side effects [0][0] / [0][1]
+// == 'safe', bit 22 the action names no position although an agent exists (reference: KeyError)
+void gc_build_grid_lut(uint32_t *lut);
+void gc_build_pair_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut,
+                       uint32_t *unsafe_rows);
 
 struct LaunchGeom {
     int blocks_per_sm_hint;
@@ -62,10 +76,12 @@ struct LaunchGeom {
 
 cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm,
                                 cudaStream_t stream);
-// fast path (S, A <= 4, deterministic): lut = 256 pair entries + 16 single-cell entries, device memory
-#define GC_PAIR_LUT_ENTRIES (256 + 16)
-cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
-                                     cudaStream_t stream);
+// fast path (S, A <= 4): lut = 1024 pair entries [fire_d][fire_c][s_c | a_c<<2 | s_d<<4 | a_d<<6] followed
+// by 32 single-cell entries [fire][s | a<<2], device memory
+#define GC_PAIR_LUT_PAIRS 1024
+#define GC_PAIR_LUT_ENTRIES (GC_PAIR_LUT_PAIRS + 32)
+cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode,
+                                     int n_sm, cudaStream_t stream);
 cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm,
                                 cudaStream_t stream);
 cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,

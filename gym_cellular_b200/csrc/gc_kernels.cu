@@ -14,7 +14,7 @@
 //   cellular step   gym_cellular/envs/cells3states3actions3.py:116-212, cells2rest3.py:103-187,
 //                   cells3resetVdeadlock.py:35-68,148-228 (via the tables built in
 //                   gym_cellular_b200/tables.py)
-//   grid world step gym_cellular/envs/grid_world.py:107-179 (closed form, see grid_step_kernel)
+//   (grid world: gc_grid.cu; fast cellular path for S, A <= 4: gc_cell_fast.cu)
 //   codec           gym_cellular/envs/utils/generalized_space_transformations.py:1-23
 #include "gc_device.cuh"
 
@@ -76,7 +76,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                         const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
                         const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
                         philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr,
-                                      static_cast<uint32_t>(c >> 2), io.seed_lo, io.seed_hi, rnd);
+                                      static_cast<uint32_t>(c >> 2), io.round_key, rnd);
                     }
                     const bool fire = (ent.x & 0x100u) && (static_cast<unsigned long long>(rnd[c & 3]) < tab.noise_thr);
                     nxt = fire ? ((ent.x >> 4) & 15u) : nxt;
@@ -134,131 +134,6 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         st_stream_u32(io.unsafe + e0, unsafe_w);
         st_stream_u32(io.count + e0, count_w);
     }
-    if (io.stats) block_flush_stats(ts, s_stats, io.stats);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Grid world step, closed form of grid_world.py:119-179 on the reference's own cellular codes
-// (grid_world.py:349-359): code_j = T_j + 4 * pos_j, T_j = tree bits (bit0 = tree at (1,0),
-// bit1 = tree at (0,0)), pos_j = row*2+col of the agent or 4 if it is not in jurisdiction j.
-//   site(p): tree bit under position p  (p=2 -> (1,0) -> bit0, p=0 -> (0,0) -> bit1, else none)
-//   1. all trees regrow (N_j = 3)                                                     :122-127
-//   2. the agent (first jurisdiction J holding one) moves to (G, q): its own jurisdiction if the
-//      action names a position there, else the first jurisdiction whose action does   :128-137
-//   3. a dead tree under the origin stays dead; a live tree under the destination dies :141-151
-//   4. jurisdictions that were barren BEFORE the step stay barren                      :154-158
-//   5. unless both were barren: one uniform draw; if < 0.01 the 2x2 bits are drawn, then the
-//      jurisdiction index, and that jurisdiction's trees are replaced                  :160-162
-//   reward = trees that died (pre-step minus post-step, clipped at 0)                  :30-39
-//   side effects row 0 = ('safe' if N_0>0 and N_1>0, 'safe' if N_0>0); never 'unsafe'  :168-179
-template <int RNG>
-__global__ void __launch_bounds__(kThreads)
-grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ StepIO io)
-{
-    __shared__ unsigned long long s_stats[5];
-    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
-    __syncthreads();
-
-    ThreadStats ts = {0, 0, 0, 0, 0};
-    bool bad_action = false;
-    const int64_t ld = io.ld;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
-    for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
-         e0 < io.end; e0 += stride) {
-        const uint32_t s0w = ld_stream_u32(io.state + e0), s1w = ld_stream_u32(io.state + ld + e0);
-        const uint32_t a0w = ld_stream_u32(io.actions + e0), a1w = ld_stream_u32(io.actions + ld + e0);
-        const int4 t4 = ld_stream_v4(io.t + e0);
-        const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
-        uint32_t n0w = 0, n1w = 0, se0w = 0, se1w = 0, trunc_w = 0, count_w = 0;
-        int tout[kEPT];
-        float rout[kEPT];
-        uint32_t iout[kEPT];
-#pragma unroll
-        for (int e = 0; e < kEPT; ++e) {
-            const bool valid = (e0 + e) < io.end;
-            const uint32_t c0 = byte_of(s0w, e), c1 = byte_of(s1w, e);
-            const uint32_t a0 = byte_of(a0w, e), a1 = byte_of(a1w, e);
-            const uint32_t T0 = c0 & 3u, T1 = c1 & 3u, P0 = c0 >> 2, P1 = c1 >> 2;
-            const bool has0 = P0 < 4u, has1 = P1 < 4u, agent = has0 || has1;
-            const uint32_t J = has0 ? 0u : 1u;
-            const uint32_t p = has0 ? P0 : P1;
-            const uint32_t TJ = has0 ? T0 : T1;
-            const uint32_t aJ = J ? a1 : a0;
-            uint32_t G, q;
-            if (aJ < 4u) { G = J; q = aJ; }
-            else if (a0 < 4u) { G = 0u; q = a0; }
-            else if (a1 < 4u) { G = 1u; q = a1; }
-            else { G = J; q = p; if (agent && valid) bad_action = true; }   // reference: KeyError
-            uint32_t N0 = 3u, N1 = 3u;
-            if (agent) {
-                const uint32_t site_p = (p == 0u ? 2u : 0u) | (p == 2u ? 1u : 0u);
-                const uint32_t site_q = (q == 0u ? 2u : 0u) | (q == 2u ? 1u : 0u);
-                const uint32_t TG = G ? T1 : T0;
-                const uint32_t kill_origin = site_p & ~TJ;            // tree site under origin, dead
-                const uint32_t kill_dest = site_q & TG;               // live tree under destination
-                if (J == 0u) N0 &= ~kill_origin; else N1 &= ~kill_origin;
-                if (G == 0u) N0 &= ~kill_dest; else N1 &= ~kill_dest;
-            }
-            const uint32_t nb = (T0 == 0u) + (T1 == 0u);
-            if (T0 == 0u) N0 = 0u;
-            if (T1 == 0u) N1 = 0u;
-            if (nb < 2u) {
-                bool trigger;
-                uint32_t b00, b10, k;
-                if (RNG == GC_RNG_REPLAY) {
-                    const double *u = io.replay + (valid ? (e0 + e) * 6 : 0);
-                    trigger = valid && (u[0] < gp.dispersal_prob);
-                    b00 = static_cast<uint32_t>(u[1] * 2.0);
-                    b10 = static_cast<uint32_t>(u[3] * 2.0);
-                    k = static_cast<uint32_t>(u[5] * 2.0);
-                } else {
-                    uint32_t rnd[4];
-                    const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
-                    const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
-                    philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr, 0u,
-                                  io.seed_lo, io.seed_hi, rnd);
-                    trigger = static_cast<unsigned long long>(rnd[0]) < gp.dispersal_thr;
-                    b00 = rnd[1] >> 31; b10 = rnd[2] >> 31; k = rnd[3] >> 31;   // floor(u * 2)
-                }
-                if (trigger) {
-                    const uint32_t Nk = b10 | (b00 << 1);
-                    if (k == 0u) N0 = Nk; else N1 = Nk;
-                }
-            }
-            const float r = static_cast<float>(__popc(T0 & ~N0) + __popc(T1 & ~N1));
-            uint32_t nc0 = N0 + 4u * ((agent && G == 0u) ? q : 4u);
-            uint32_t nc1 = N1 + 4u * ((agent && G == 1u) ? q : 4u);
-            const uint32_t se0 = (N0 > 0u && N1 > 0u) ? 1u : 0u, se1 = (N0 > 0u) ? 1u : 0u;
-            int tn = tin[e] + 1;
-            uint32_t tr = 0;
-            if (io.max_episode_steps > 0 && tn >= io.max_episode_steps) {
-                tr = 1; tn = 0; nc0 = 15u; nc1 = 18u;                  // grid_world.py:238-259
-            }
-            n0w |= nc0 << (8 * e); n1w |= nc1 << (8 * e);
-            se0w |= se0 << (8 * e); se1w |= se1 << (8 * e);
-            trunc_w |= tr << (8 * e); count_w |= nb << (8 * e);
-            tout[e] = tn; rout[e] = r; iout[e] = nc0 + 20u * nc1;
-            if (valid) {
-                ts.steps += 1; ts.count += nb; ts.truncated += tr;
-                ts.reward_q24 += static_cast<long long>(r) << 24;
-            }
-        }
-        st_stream_u32(io.state + e0, n0w);
-        st_stream_u32(io.state + ld + e0, n1w);
-        if (io.se_row) {
-            st_stream_u32(io.se_row + e0, se0w);
-            st_stream_u32(io.se_row + ld + e0, se1w);
-        }
-        st_stream_v4(io.t + e0, make_int4(tout[0], tout[1], tout[2], tout[3]));
-        st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
-                                               __float_as_int(rout[2]), __float_as_int(rout[3])));
-        st_stream_v4(io.index + e0, make_int4(iout[0], iout[1], iout[2], iout[3]));
-        st_stream_u32(io.terminated + e0, 0u);
-        st_stream_u32(io.truncated + e0, trunc_w);
-        st_stream_u32(io.unsafe + e0, 0u);
-        st_stream_u32(io.count + e0, count_w);
-    }
-    if (bad_action) atomicOr(io.status, 1ull);
     if (io.stats) block_flush_stats(ts, s_stats, io.stats);
 }
 
@@ -342,13 +217,13 @@ cudaError_t launch_cell_c(const CellTables &tab, const StepIO &io, int rng_mode,
     const int64_t n = io.end - io.begin;
     switch (rng_mode) {
     case GC_RNG_NONE:
-        cell_step_kernel<C, GC_RNG_NONE><<<grid_for(cell_step_kernel<C, GC_RNG_NONE>, n, n_sm), kThreads, 0, st>>>(tab, io);
+        cell_step_kernel<C, GC_RNG_NONE><<<grid_for<cell_step_kernel<C, GC_RNG_NONE>>(n, n_sm), kThreads, 0, st>>>(tab, io);
         break;
     case GC_RNG_PHILOX:
-        cell_step_kernel<C, GC_RNG_PHILOX><<<grid_for(cell_step_kernel<C, GC_RNG_PHILOX>, n, n_sm), kThreads, 0, st>>>(tab, io);
+        cell_step_kernel<C, GC_RNG_PHILOX><<<grid_for<cell_step_kernel<C, GC_RNG_PHILOX>>(n, n_sm), kThreads, 0, st>>>(tab, io);
         break;
     default:
-        cell_step_kernel<C, GC_RNG_REPLAY><<<grid_for(cell_step_kernel<C, GC_RNG_REPLAY>, n, n_sm), kThreads, 0, st>>>(tab, io);
+        cell_step_kernel<C, GC_RNG_REPLAY><<<grid_for<cell_step_kernel<C, GC_RNG_REPLAY>>(n, n_sm), kThreads, 0, st>>>(tab, io);
         break;
     }
     return cudaGetLastError();
@@ -365,16 +240,6 @@ cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng
 #undef GC_CASE
     default: return cudaErrorInvalidValue;
     }
-}
-
-cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
-{
-    const int64_t n = io.end - io.begin;
-    if (rng_mode == GC_RNG_REPLAY)
-        grid_step_kernel<GC_RNG_REPLAY><<<grid_for(grid_step_kernel<GC_RNG_REPLAY>, n, n_sm), kThreads, 0, st>>>(gp, io);
-    else
-        grid_step_kernel<GC_RNG_PHILOX><<<grid_for(grid_step_kernel<GC_RNG_PHILOX>, n, n_sm), kThreads, 0, st>>>(gp, io);
-    return cudaGetLastError();
 }
 
 cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,
