@@ -153,19 +153,14 @@ def build_batches(workload, device, rank, n_override=None, env_scale=1.0):
             else:
                 a = torch.randint(0, env.n_actions, (env.n_cells, env.ld), dtype=torch.int8, device=device, generator=gen)
             ring.append(a)
-        batches.append(dict(env=env, ring=ring, kind=kind, n=n, bytes=bytes_per_env_step(kind, env.n_cells)))
+        batches.append(dict(env=env, ring=ring, kind=kind, n=n, bytes=bytes_per_env_step(kind, env.n_cells),
+                            calls=[env.bind_step(a) for a in ring]))
     return batches
 
 
 def launch_step(batch, i):
     """One device-path step: actions already resident; a single ctypes call = a single kernel."""
-    import ctypes as C
-    env, a = batch["env"], batch["ring"][i % RING]
-    from gym_cellular_b200 import _lib
-    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-    _lib.check(env._lib.gc_step(env._h, 0, env.num_envs, p(a), p(env._state), p(env._t), p(env._reward), p(env._index),
-                                p(env._terminated), p(env._truncated), p(env._unsafe), p(env._count), None, None,
-                                p(env._stats), env._stream()))
+    batch["calls"][i % RING]()
 
 
 def time_device_path(batches, steps, warmup, dist, device, sampler_index):

@@ -44,7 +44,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [path] + HEADERS):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            extra = os.environ.get("GC_NVCC_EXTRA", "").split()       # e.g. -DGC_PAIR_MINB_WIDE=1 (tuning runs)
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:

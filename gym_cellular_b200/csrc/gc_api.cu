@@ -137,6 +137,8 @@ int gc_create(const gc_config *cfg, gc_env **out)
     if (cfg->ld < cfg->n_envs || cfg->ld % 16 != 0)
         return fail(GC_ERR_INVALID, "ld must be a multiple of 16 and >= n_envs");
     if (cfg->max_episode_steps < 0) return fail(GC_ERR_INVALID, "max_episode_steps must be >= 0");
+    if (cfg->env_id_offset < 0 || cfg->env_id_offset % 4 != 0)
+        return fail(GC_ERR_INVALID, "env_id_offset must be a non-negative multiple of 4");
     if (cfg->kind == GC_KIND_CELLULAR) {
         if (cfg->n_cells < 1 || cfg->n_cells > GC_MAX_CELLS)
             return fail(GC_ERR_INVALID, "n_cells must be in 1..%d", GC_MAX_CELLS);

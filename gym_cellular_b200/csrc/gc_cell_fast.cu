@@ -25,15 +25,127 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 // resident blocks per SM the register budget is sized for: all 2C row words of a thread's 4 envs are
 // requested up front (memory-level parallelism), so wide envs trade occupancy for loads in flight
-constexpr int pair_min_blocks(int c) { return c > 8 ? 2 : (c > 4 ? 3 : 4); }
+#ifndef GC_PAIR_MINB
+#define GC_PAIR_MINB 4
+#endif
+// resident blocks per SM the register budget is sized for; the Philox variants of wide envs carry
+// 16 more registers (one random block per env) and get the budget of three blocks
+constexpr int pair_min_blocks(int c, int rng) { return (rng == GC_RNG_PHILOX && c > 4) ? 3 : GC_PAIR_MINB; }
 
+// Everything a thread carries across the cell groups of its four envs.
+struct EnvAcc {
+    float r[kEPT];          // reward sums
+    uint32_t add[kEPT];     // sum of info words: bits 0-4 = counted cells
+    uint32_t orr[kEPT];     // OR of info words of the cells j >= 2: bits 8-11 = levels present
+    uint32_t first[kEPT];   // info word of the pair (cell 0, cell 1) (or of cell 0 alone when C == 1)
+    uint32_t idx[kEPT];     // tabular index
+};
+
+// One group of N <= 4 consecutive cells starting at cell c0 (c0 % 4 == 0) for the 4 envs of a thread.
+//   sw / aw : state / action words of the N cells (byte lane e = env e)
+//   FIRST   : the group holds cell 0
+template <int N, int C, int RNG, bool WITH_SE, bool FIRST>
+__device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io, const uint2 *s_pair,
+                                         const uint2 *s_single, const uint8_t (*s_se)[GC_TBL], int c0,
+                                         int64_t e0, int rem, uint32_t gid_lo, uint32_t gid_hi,
+                                         const int (&tin)[kEPT], uint32_t keep, const uint32_t (&sw)[4],
+                                         const uint32_t (&aw)[4], EnvAcc &acc)
+{
+    uint32_t rnd[kEPT][4];
+    if (RNG == GC_RNG_PHILOX) {
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+            philox4x32_10(gid_lo | e, gid_hi, ctr, static_cast<uint32_t>(c0 >> 2), io.round_key, rnd[e]);
+        }
+    }
+    // did the noise draw of cell (c0 + i) fire for env e?  (the table ignores it where no draw is consumed)
+    auto fire = [&](int e, int i) -> uint32_t {
+        if (RNG == GC_RNG_PHILOX) return (tab.noise_thr_nz && rnd[e][i] <= tab.noise_thr_m1) ? 1u : 0u;
+        if (RNG == GC_RNG_REPLAY) return (e < rem && io.replay[(e0 + e) * C + c0 + i] < tab.noise_prob) ? 1u : 0u;
+        return 0u;
+    };
+    const int64_t ld = io.ld;
+    uint32_t q = 0;                       // index digits of the group folded into one byte per env
+    uint32_t rows[4];
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        const bool pair = i + 1 < N;
+        uint32_t inf[kEPT];
+        if (pair) {
+            const uint32_t pidx = ((aw[i + 1] & 0x03030303u) * 4u + (sw[i + 1] & 0x03030303u)) * 16u +
+                                  (aw[i] & 0x03030303u) * 4u + (sw[i] & 0x03030303u);
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                uint32_t ix = byte_of(pidx, e);
+                if (RNG != GC_RNG_NONE) ix |= (fire(e, i) << 8) | (fire(e, i + 1) << 9);
+                const uint2 ent = s_pair[ix];
+                acc.r[e] += __uint_as_float(ent.y);
+                inf[e] = ent.x;
+            }
+        } else {
+            const uint32_t sidx = (aw[i] & 0x03030303u) * 4u + (sw[i] & 0x03030303u);
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                uint32_t ix = byte_of(sidx, e) & 15u;
+                if (RNG != GC_RNG_NONE) ix |= fire(e, i) << 4;
+                const uint2 ent = s_single[ix];
+                acc.r[e] += __uint_as_float(ent.y);
+                inf[e] = ent.x;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            acc.add[e] += inf[e];
+            if (FIRST && i == 0) acc.first[e] = inf[e]; else acc.orr[e] |= inf[e];
+        }
+        // SoA rows of the next state: byte 2 (cell c0+i) and byte 3 (cell c0+i+1) of the four info words
+        const uint32_t u = prmt(inf[0], inf[1], 0x7362), v = prmt(inf[2], inf[3], 0x7362);
+        rows[i] = prmt(u, v, 0x5410);
+        if (pair) rows[i + 1] = prmt(u, v, 0x7632);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (WITH_SE) {
+            // row 0 of the side-effects matrix from the (pre-reset) next state: entry j from
+            // (s'_0, s'_p), p = 1 for j = 0 (cell 0 and its partner live in the first group)
+            uint32_t sew = 0;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                const uint32_t s0n = (acc.first[e] >> 16) & 0xFFu;
+                const uint32_t partner = (FIRST && i == 0) ? ((C > 1) ? (acc.first[e] >> 24) : s0n) : byte_of(rows[i], e);
+                sew |= static_cast<uint32_t>(s_se[c0 + i][(s0n * GC_LVL_PAD + partner) & (GC_TBL - 1)]) << (8 * e);
+            }
+            st_stream_u32(io.se_row + (c0 + i) * ld + e0, sew);
+        }
+        const uint32_t out = (rows[i] & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c0 + i])) & ~keep);
+        st_stream_u32(io.state + (c0 + i) * ld + e0, out);
+        q += out * tab.place4[i];
+    }
+    const uint32_t place = tab.place[c0];
+#pragma unroll
+    for (int e = 0; e < kEPT; ++e) acc.idx[e] += byte_of(q, e) * place;
+}
+
+template <int N>
+__device__ __forceinline__ void load_cells(const StepIO &io, int c0, int64_t e0, uint32_t (&sw)[4], uint32_t (&aw)[4])
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        sw[i] = ld_stream_u32(io.state + (c0 + i) * io.ld + e0);
+        aw[i] = ld_stream_u32(io.actions + (c0 + i) * io.ld + e0);
+    }
+}
+
+// The cells of an env are walked in groups of four (two table lookups per env and group) by a
+// software-pipelined loop: the rows of group g+1 are requested before group g is computed, so a
+// thread keeps 8-16 row words in flight with ~60 registers and four blocks stay resident per SM.
 template <int C, int RNG, bool WITH_SE>
-__global__ void __launch_bounds__(kThreads, pair_min_blocks(C))
+__global__ void __launch_bounds__(kThreads, pair_min_blocks(C, RNG))
 cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ StepIO io,
                  const uint2 *__restrict__ lut)
 {
-    constexpr int NP = C / 2;
-    constexpr bool ODD = (C & 1) != 0;
+    constexpr int NG = C / 4, R = C % 4;                        // full groups, cells in the tail group
     constexpr int N_PAIR = (RNG == GC_RNG_NONE) ? 256 : GC_PAIR_LUT_PAIRS;
     constexpr int N_SINGLE = (RNG == GC_RNG_NONE) ? 16 : 32;
     __shared__ uint2 s_pair[N_PAIR];
@@ -48,142 +160,82 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
-    ThreadStats ts = {0, 0, 0, 0, 0};
-    const int64_t ld = io.ld;
+    uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;   // < 2^32 per thread and launch
+    long long st_reward = 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
     for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
          e0 < io.end; e0 += stride) {
-        uint32_t sw[C], aw[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            sw[c] = ld_stream_u32(io.state + c * ld + e0);
-            aw[c] = ld_stream_u32(io.actions + c * ld + e0) & 0x03030303u;   // keep byte lanes apart
-        }
+        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);    // envs of this word in range
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);           // multiple of 4: | e never carries
+        const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
+
+        uint32_t sa[4], aa[4], sb[4], ab[4];
+        if (NG > 0) load_cells<4>(io, 0, e0, sa, aa); else load_cells<R>(io, 0, e0, sa, aa);
         const int4 t4 = ld_stream_v4(io.t + e0);
+        if (NG > 1) load_cells<4>(io, 4, e0, sb, ab); else if (NG == 1 && R > 0) load_cells<R>(io, 4, e0, sb, ab);
+
         const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
         int tn[kEPT] = {t4.x + 1, t4.y + 1, t4.z + 1, t4.w + 1};
-        uint32_t rnd[kEPT][4];                                     // Philox block of the current 4 cells
         uint32_t trunc_w = 0, keep = 0xFFFFFFFFu;                 // keep: byte mask of envs NOT reset
         if (io.max_episode_steps > 0) {
 #pragma unroll
             for (int e = 0; e < kEPT; ++e)
                 if (tn[e] >= io.max_episode_steps) { tn[e] = 0; trunc_w |= 1u << (8 * e); keep &= ~(0xFFu << (8 * e)); }
         }
+        EnvAcc acc;
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.add[e] = 0; acc.orr[e] = 0; acc.first[e] = 0; acc.idx[e] = 0; }
 
-        float r[kEPT] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t add[kEPT] = {0, 0, 0, 0}, orr[kEPT] = {0, 0, 0, 0}, first[kEPT];
-        uint32_t idx[kEPT] = {0, 0, 0, 0};
-        uint32_t raw[WITH_SE ? C : 1];
-        uint32_t q = 0;                                            // 4 cells' worth of index digits per byte
+        if (NG == 0) {
+            do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, tin, keep, sa, aa, acc);
+        } else {
+            do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, tin, keep, sa, aa, acc);
+#pragma unroll 1
+            for (int g = 1; g < NG; ++g) {
 #pragma unroll
-        for (int k = 0; k < NP + (ODD ? 1 : 0); ++k) {
-            const int c = 2 * k, d = 2 * k + 1;
-            const bool pair = k < NP;
-            uint32_t inf[kEPT];
-            if (RNG == GC_RNG_PHILOX && (c & 3) == 0) {
-#pragma unroll
-                for (int e = 0; e < kEPT; ++e) {
-                    const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
-                    const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
-                    philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr,
-                                  static_cast<uint32_t>(c >> 2), io.round_key, rnd[e]);
-                }
+                for (int i = 0; i < 4; ++i) { sa[i] = sb[i]; aa[i] = ab[i]; }
+                if (g + 1 < NG) load_cells<4>(io, 4 * (g + 1), e0, sb, ab);
+                else if (R > 0) load_cells<R>(io, 4 * NG, e0, sb, ab);
+                do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, tin, keep, sa, aa, acc);
             }
-            // fire(e, cell): did the noise draw of that cell fire?  (ignored by the table where the
-            // (level, action) pair consumes no draw)
-            auto fire = [&](int e, int cell) -> uint32_t {
-                if (RNG == GC_RNG_PHILOX) return (tab.noise_thr_nz && rnd[e][cell & 3] <= tab.noise_thr_m1) ? 1u : 0u;
-                if (RNG == GC_RNG_REPLAY)
-                    return ((e0 + e) < io.end && io.replay[(e0 + e) * C + cell] < tab.noise_prob) ? 1u : 0u;
-                return 0u;
-            };
-            if (pair) {
-                const uint32_t pidx = (aw[d] * 4u + (sw[d] & 0x03030303u)) * 16u + aw[c] * 4u + (sw[c] & 0x03030303u);
-#pragma unroll
-                for (int e = 0; e < kEPT; ++e) {
-                    uint32_t ix = byte_of(pidx, e);
-                    if (RNG != GC_RNG_NONE) ix |= (fire(e, c) << 8) | (fire(e, d) << 9);
-                    const uint2 ent = s_pair[ix];
-                    r[e] += __uint_as_float(ent.y);
-                    inf[e] = ent.x;
-                }
-            } else {
-                const uint32_t sidx = aw[c] * 4u + (sw[c] & 0x03030303u);
-#pragma unroll
-                for (int e = 0; e < kEPT; ++e) {
-                    uint32_t ix = byte_of(sidx, e) & 15u;
-                    if (RNG != GC_RNG_NONE) ix |= fire(e, c) << 4;
-                    const uint2 ent = s_single[ix];
-                    r[e] += __uint_as_float(ent.y);
-                    inf[e] = ent.x;
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < kEPT; ++e) {
-                add[e] += inf[e];
-                if (k == 0) first[e] = inf[e]; else orr[e] |= inf[e];
-            }
-            // SoA rows of the next state: byte 2 (cell c) and byte 3 (cell d) of the four info words
-            const uint32_t u = prmt(inf[0], inf[1], 0x7362), v = prmt(inf[2], inf[3], 0x7362);
-            const uint32_t row_c = prmt(u, v, 0x5410), row_d = prmt(u, v, 0x7632);
-            if (WITH_SE) { raw[c] = row_c; if (pair) raw[d] = row_d; }
-            const uint32_t out_c = (row_c & keep) | (0x01010101u * static_cast<uint8_t>(tab.init[c]) & ~keep);
-            st_stream_u32(io.state + c * ld + e0, out_c);
-            // index digits: q collects cells 4g..4g+3 as one base-S^4 digit per env byte
-            q += out_c * tab.place4[c & 3];
-            if (pair) {
-                const uint32_t out_d = (row_d & keep) | (0x01010101u * static_cast<uint8_t>(tab.init[d]) & ~keep);
-                st_stream_u32(io.state + d * ld + e0, out_d);
-                q += out_d * tab.place4[d & 3];
-            }
-            if ((k & 1) == 1 || k == NP + (ODD ? 1 : 0) - 1) {     // a group of 4 cells is complete
-#pragma unroll
-                for (int e = 0; e < kEPT; ++e) idx[e] += byte_of(q, e) * tab.place[(c / 4) * 4];
-                q = 0;
-            }
+            if (R > 0)
+                do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, tin, keep, sb, ab, acc);
         }
 
         uint32_t unsafe_w = 0, count_w = 0;
         float rout[kEPT];
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
-            const uint32_t s0n = (first[e] >> 16) & 3u;
+            const uint32_t s0n = (acc.first[e] >> 16) & 3u;
             const uint32_t rowmask = (tab.unsafe_rows >> (8 * s0n)) & 0xFFu;
-            const uint32_t uns = ((first[e] >> 12) & 1u) | ((((orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
-            const uint32_t cnt = add[e] & 31u;
-            float rr = r[e];
+            const uint32_t uns = ((acc.first[e] >> 12) & 1u) | ((((acc.orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
+            const uint32_t cnt = acc.add[e] & 31u;
+            float rr = acc.r[e];
             if (tab.reward_log2) rr = log1pf(rr) * 1.44269504088896341f;
             rout[e] = rr;
             unsafe_w |= uns << (8 * e); count_w |= cnt << (8 * e);
-            if ((e0 + e) < io.end) {
-                ts.steps += 1; ts.unsafe += uns; ts.count += cnt; ts.truncated += (trunc_w >> (8 * e)) & 1u;
-                ts.reward_q24 += __float2ll_rn(rr * 16777216.0f);
-            }
+            if (e < rem) st_reward += __float2int_rn(rr * 16777216.0f);          // |reward| < 128
         }
-        if (WITH_SE) {
-            // row 0 of the side-effects matrix from the (pre-reset) next state
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                uint32_t sew = 0;
-#pragma unroll
-                for (int e = 0; e < kEPT; ++e) {
-                    const uint32_t s0n = byte_of(raw[0], e);
-                    const uint32_t partner = byte_of(raw[c == 0 ? (C > 1 ? 1 : 0) : c], e);
-                    sew |= static_cast<uint32_t>(s_se[c][(s0n * GC_LVL_PAD + partner) & (GC_TBL - 1)]) << (8 * e);
-                }
-                st_stream_u32(io.se_row + c * ld + e0, sew);
-            }
+        {
+            const uint32_t vb = valid_bytes(rem);
+            st_steps += rem;
+            st_unsafe = add_bytes(unsafe_w & vb, st_unsafe);
+            st_count = add_bytes(count_w & vb, st_count);
+            st_trunc = add_bytes(trunc_w & vb, st_trunc);
         }
         st_stream_v4(io.t + e0, make_int4(tn[0], tn[1], tn[2], tn[3]));
         st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
                                                __float_as_int(rout[2]), __float_as_int(rout[3])));
-        st_stream_v4(io.index + e0, make_int4(idx[0], idx[1], idx[2], idx[3]));
+        st_stream_v4(io.index + e0, make_int4(acc.idx[0], acc.idx[1], acc.idx[2], acc.idx[3]));
         st_stream_u32(io.terminated + e0, 0u);
         st_stream_u32(io.truncated + e0, trunc_w);
         st_stream_u32(io.unsafe + e0, unsafe_w);
         st_stream_u32(io.count + e0, count_w);
     }
-    if (io.stats) block_flush_stats(ts, s_stats, io.stats);
+    if (io.stats) {
+        const ThreadStats ts = {st_steps, st_unsafe, st_count, st_trunc, st_reward};
+        block_flush_stats(ts, s_stats, io.stats);
+    }
 }
 
 template <int C, int RNG>

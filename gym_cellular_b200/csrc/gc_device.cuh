@@ -47,6 +47,12 @@ struct ThreadStats {
     long long reward_q24;
 };
 
+// byte mask of the envs of a 4-env word that lie inside the launch range (rem = envs left, >= 1)
+__device__ __forceinline__ uint32_t valid_bytes(int rem) { return rem >= 4 ? 0xFFFFFFFFu : ((1u << (8 * rem)) - 1u); }
+
+// sum of the four bytes of w added to acc (one IDP.4A)
+__device__ __forceinline__ uint32_t add_bytes(uint32_t w, uint32_t acc) { return __dp4a(w, 0x01010101u, acc); }
+
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 {
 #pragma unroll

@@ -26,12 +26,13 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
-    ThreadStats ts = {0, 0, 0, 0, 0};
-    bool bad_action = false;
+    uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     const int64_t ld = io.ld;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
     for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
          e0 < io.end; e0 += stride) {
+        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
         const uint32_t s0w = ld_stream_u32(io.state + e0), s1w = ld_stream_u32(io.state + ld + e0);
         uint32_t a0w = ld_stream_u32(io.actions + e0), a1w = ld_stream_u32(io.actions + ld + e0);
         const int4 t4 = ld_stream_v4(io.t + e0);
@@ -51,7 +52,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         for (int e = 0; e < kEPT; ++e) {
             const uint32_t nb = (ent[e] >> 18) & 3u;
             if (nb < 2u) {                                           // grid_world.py:160
-                const bool valid = (e0 + e) < io.end;
+                const bool valid = e < rem;
                 bool trigger;
                 uint32_t b00, b10, k;
                 if (RNG == GC_RNG_REPLAY) {
@@ -62,9 +63,8 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
                     k = static_cast<uint32_t>(u[5] * 2.0);
                 } else {
                     uint32_t rnd[4];
-                    const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
                     const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
-                    philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr, 0u,
+                    philox4x32_10(static_cast<uint32_t>(gid0) | e, static_cast<uint32_t>(gid0 >> 32), ctr, 0u,
                                   io.round_key, rnd);
                     trigger = gp.dispersal_thr_nz && (rnd[0] <= gp.dispersal_thr_m1);
                     b00 = rnd[1] >> 31; b10 = rnd[2] >> 31; k = rnd[3] >> 31;       // floor(u * 2)
@@ -83,29 +83,31 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
                 }
             }
         }
-        uint32_t trunc_w = 0, count_w = 0, se0w = 0, se1w = 0;
+        uint32_t trunc_w = 0, count_w = 0, se0w = 0, se1w = 0, rew_w = 0;
         int tout[kEPT];
         float rout[kEPT];
         uint32_t iout[kEPT];
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
-            const bool valid = (e0 + e) < io.end;
             const uint32_t rew = (ent[e] >> 16) & 3u, nb = (ent[e] >> 18) & 3u;
             int tn = tin[e] + 1;
             uint32_t tr = 0;
-            if (valid && (ent[e] & (1u << 22))) bad_action = true;
+            if (e < rem) bad_bits |= ent[e];
             if (io.max_episode_steps > 0 && tn >= io.max_episode_steps) {
                 tr = 1; tn = 0;
                 ent[e] = (ent[e] & 0xFFFF0000u) | 15u | (18u << 8);               // grid_world.py:238-259
             }
             tout[e] = tn; rout[e] = static_cast<float>(rew);
             iout[e] = (ent[e] & 0xFFu) + 20u * ((ent[e] >> 8) & 0xFFu);
-            trunc_w |= tr << (8 * e); count_w |= nb << (8 * e);
+            trunc_w |= tr << (8 * e); count_w |= nb << (8 * e); rew_w |= rew << (8 * e);
             se0w |= ((ent[e] >> 20) & 1u) << (8 * e); se1w |= ((ent[e] >> 21) & 1u) << (8 * e);
-            if (valid) {
-                ts.steps += 1; ts.count += nb; ts.truncated += tr;
-                ts.reward_q24 += static_cast<long long>(rew) << 24;
-            }
+        }
+        {
+            const uint32_t vb = valid_bytes(rem);
+            st_steps += rem;
+            st_count = add_bytes(count_w & vb, st_count);
+            st_trunc = add_bytes(trunc_w & vb, st_trunc);
+            st_reward = add_bytes(rew_w & vb, st_reward);
         }
         // SoA rows of the next state: byte 0 / byte 1 of the four entries
         const uint32_t u = prmt(ent[0], ent[1], 0x5140), v = prmt(ent[2], ent[3], 0x5140);
@@ -124,8 +126,11 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         st_stream_u32(io.unsafe + e0, 0u);                          // never 'unsafe': grid_world.py:174-175
         st_stream_u32(io.count + e0, count_w);
     }
-    if (bad_action) atomicOr(io.status, 1ull);
-    if (io.stats) block_flush_stats(ts, s_stats, io.stats);
+    if (bad_bits & (1u << 22)) atomicOr(io.status, 1ull);
+    if (io.stats) {
+        const ThreadStats ts = {st_steps, 0, st_count, st_trunc, static_cast<long long>(st_reward) << 24};
+        block_flush_stats(ts, s_stats, io.stats);
+    }
 }
 
 }  // namespace

@@ -270,6 +270,26 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
             _ptr(self._se_row), _ptr(ru), _ptr(self._stats), self._stream()))
 
+    def bind_step(self, actions=None):
+        """Returns a zero-argument callable that launches one step on the current stream with all
+        ctypes arguments pre-bound (for tight rollout loops: ~2 us of host time per step).
+        `actions`: an int8 device tensor [n_cells, ld] kept alive by the caller, or None for
+        `action_buffer`."""
+        a = self._actions if actions is None else actions
+        if a.dtype != torch.int8 or a.shape != (self.n_cells, self.ld) or not a.is_contiguous() or a.device != self.device:
+            raise ValueError(f"bind_step needs a contiguous int8 tensor of shape {(self.n_cells, self.ld)} on {self.device}")
+        fn, check, dev = self._lib.gc_step, _lib.check, self.device
+        args = (self._h, 0, self.num_envs, _ptr(a), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
+                _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe),
+                _ptr(self._count), _ptr(self._se_row), None, _ptr(self._stats))
+        current_stream = torch.cuda.current_stream
+
+        def launch():
+            rc = fn(*args, current_stream(dev).cuda_stream)
+            if rc:
+                check(rc)
+        return launch
+
     @property
     def action_buffer(self):
         """int8 [n_cells, num_envs] device view: write actions here and call step_device()."""
