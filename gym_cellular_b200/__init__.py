@@ -7,7 +7,14 @@ from ._gym import gym  # noqa: F401  (real gymnasium, or the structural stand-in
 from . import tables
 from .tables import right_polarizing, multiple_optima, nonlinear, nonlinear_right_polarizing
 from .vector_env import CellularVectorEnv, make_vector_env
+from .codec import (generalized_cellular2tabular, generalized_tabular2cellular, cellular2tabular,
+                    tabular2cellular)
+from .envs import (Cells3States3Actions3Env, Cells2Rest3Env, Cells3ResetVDeadlockEnv, GridWorldEnv,
+                   PriorKnowledge, GridWorldPriorKnowledge)
+from . import registration  # noqa: F401  (registers the gym_cellular/<Name>-v0 ids)
 
 __all__ = ["CellularVectorEnv", "make_vector_env", "tables", "right_polarizing", "multiple_optima",
-           "nonlinear", "nonlinear_right_polarizing"]
+           "nonlinear", "nonlinear_right_polarizing", "Cells3States3Actions3Env", "Cells2Rest3Env",
+           "Cells3ResetVDeadlockEnv", "GridWorldEnv", "PriorKnowledge", "GridWorldPriorKnowledge",
+           "generalized_cellular2tabular", "generalized_tabular2cellular", "cellular2tabular", "tabular2cellular"]
 __version__ = "0.1.0"

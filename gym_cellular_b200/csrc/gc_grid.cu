@@ -4,8 +4,8 @@
 // the side-effect report -- is a function of (code_0, code_1, a_0, a_1) with 20*20*5*5 = 10,000
 // cases; the host tabulates it once (gc_tables.cu: gc_build_grid_lut, closed form of :119-158) and
 // each block stages the 40 KB table into shared memory.  Per env-step the kernel does one shared
-// load; the seed-dispersal event (:160-162, probability 0.01, one Philox block per env-step unless
-// both jurisdictions are barren) patches the looked-up result in-line.
+// load; the seed-dispersal event (:160-162, probability 0.01; the trigger draws of four envs share one
+// Philox block) patches the looked-up result in-line.
 #include "gc_device.cuh"
 
 namespace {
@@ -48,13 +48,35 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             const uint32_t ix = tab * 25u + byte_of(actw, e);
             ent[e] = s_lut[ix < GC_GRID_LUT_ENTRIES ? ix : 0];
         }
+        // Seed dispersal (grid_world.py:160-162): unless both jurisdictions were barren, one uniform
+        // draw; below dispersal_prob the 2x2 bits and the jurisdiction index are drawn as well.  The
+        // trigger words of the four envs of a thread are the four words of ONE Philox block (keyed by
+        // global env id / 4) whenever they share the RNG counter, which they always do unless
+        // episodic counters have drifted apart.
+        uint32_t trig[kEPT];
+        if (RNG == GC_RNG_PHILOX) {
+            const uint64_t grp = gid0 >> 2;
+            const bool same_t = !io.episodic || (tin[0] == tin[1] && tin[1] == tin[2] && tin[2] == tin[3]);
+            if (same_t) {
+                const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[0]) : io.rng_counter;
+                philox4x32_10(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32), ctr, 0u, io.round_key, trig);
+            } else {
+#pragma unroll 1
+                for (int e = 0; e < kEPT; ++e) {
+                    uint32_t w[4];
+                    philox4x32_10(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32),
+                                  static_cast<uint32_t>(tin[e]), 0u, io.round_key, w);
+                    trig[e] = w[e];
+                }
+            }
+        }
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
             const uint32_t nb = (ent[e] >> 18) & 3u;
-            if (nb < 2u) {                                           // grid_world.py:160
+            if (nb < 2u) {
                 const bool valid = e < rem;
                 bool trigger;
-                uint32_t b00, b10, k;
+                uint32_t b00 = 0, b10 = 0, k = 0;
                 if (RNG == GC_RNG_REPLAY) {
                     const double *u = io.replay + (valid ? (e0 + e) * 6 : 0);
                     trigger = valid && (u[0] < gp.dispersal_prob);
@@ -62,14 +84,16 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
                     b10 = static_cast<uint32_t>(u[3] * 2.0);
                     k = static_cast<uint32_t>(u[5] * 2.0);
                 } else {
-                    uint32_t rnd[4];
-                    const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
-                    philox4x32_10(static_cast<uint32_t>(gid0) | e, static_cast<uint32_t>(gid0 >> 32), ctr, 0u,
-                                  io.round_key, rnd);
-                    trigger = gp.dispersal_thr_nz && (rnd[0] <= gp.dispersal_thr_m1);
-                    b00 = rnd[1] >> 31; b10 = rnd[2] >> 31; k = rnd[3] >> 31;       // floor(u * 2)
+                    trigger = gp.dispersal_thr_nz && (trig[e] <= gp.dispersal_thr_m1);
                 }
                 if (trigger) {
+                    if (RNG == GC_RNG_PHILOX) {
+                        uint32_t w[4];
+                        const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+                        philox4x32_10(static_cast<uint32_t>(gid0) | e, static_cast<uint32_t>(gid0 >> 32), ctr, 1u,
+                                      io.round_key, w);
+                        b00 = w[0] >> 31; b10 = w[1] >> 31; k = w[2] >> 31;          // floor(u * 2)
+                    }
                     // the drawn 2x2 bits (times tree_positions) replace jurisdiction k's trees: :162
                     const uint32_t T0 = byte_of(s0w, e) & 3u, T1 = byte_of(s1w, e) & 3u;
                     uint32_t nc0 = ent[e] & 0xFFu, nc1 = (ent[e] >> 8) & 0xFFu;

@@ -59,11 +59,14 @@ typedef struct {
  * device RNG layer is new (the reference uses numpy's global MT19937); this is its CPU twin.
  * word(env, t, w) = philox(key = seed, ctr = (env_lo, env_hi, t, w / 4))[w % 4]
  * and the uniform handed to the reference-style comparison is u = word * 2^-32 (exact).
- * Cellular family: draw slot c (cell c) uses word c.  Grid world: the six draws of a step in
- * reference order (trigger, b00, b01, b10, b11, k) use words 0, 1, 4, 2, 5, 3, so that the four
- * draws that can matter (b01 and b11 are multiplied by tree_positions == 0) share one block.
+ * Cellular family: draw slot c (cell c) uses word c of the env's own stream.
+ * Grid world: the trigger draw of env g is word (g % 4) of the block shared by the four envs
+ * g/4*4 .. g/4*4+3:  philox(key, ctr = ((g/4)_lo, (g/4)_hi, t, 0))[g % 4]  (one Philox block per
+ * four env-steps); the five integers drawn when the trigger fires (b00, b01, b10, b11, k in
+ * reference order) come from the env's own stream philox(key, ctr = (g_lo, g_hi, t, 1 + w/4))[w%4]
+ * with w = 0, 3, 1, 4, 2 (b01 and b11 are multiplied by tree_positions == 0, so block 1 suffices).
  */
-static const int GW_SLOT_WORD[6] = {0, 1, 4, 2, 5, 3};
+static const int GW_SLOT_WORD[6] = {-1, 0, 3, 1, 4, 2};
 
 static void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
 {
@@ -102,11 +105,20 @@ static double draw_uniform(draw_src *d, int slot)
 {
     if (d->cfg->flags & GCO_F_REPLAY)
         return d->replay[slot];
-    if (d->cfg->kind == GCO_KIND_GRIDWORLD) slot = GW_SLOT_WORD[slot];
+    uint32_t key[2] = {(uint32_t)d->cfg->seed, (uint32_t)(d->cfg->seed >> 32)};
+    if (d->cfg->kind == GCO_KIND_GRIDWORLD) {
+        if (slot == 0) {                                      /* trigger: block shared by 4 envs */
+            uint64_t grp = d->env_id >> 2;
+            uint32_t ctr[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), d->t, 0u};
+            uint32_t w[4];
+            philox4x32_10(ctr, key, w);
+            return (double)w[d->env_id & 3] * (1.0 / 4294967296.0);
+        }
+        slot = GW_SLOT_WORD[slot] + 4;                        /* own stream, blocks 1.. */
+    }
     int blk = slot >> 2;
     if (blk != d->cached_block) {
         uint32_t ctr[4] = {(uint32_t)d->env_id, (uint32_t)(d->env_id >> 32), d->t, (uint32_t)blk};
-        uint32_t key[2] = {(uint32_t)d->cfg->seed, (uint32_t)(d->cfg->seed >> 32)};
         philox4x32_10(ctr, key, d->words);
         d->cached_block = blk;
     }
