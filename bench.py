@@ -320,10 +320,9 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
     n_rank = sum(b["n"] for b in batches)
     ms, launches, clocks = time_device_path(batches, steps, warmup, dist, device, device.index)
     el_host, h2d, d2h = time_host_path(batches, e2e_steps, 2, dist, device)
-    stats = torch.stack([b["env"]._stats for b in batches]).sum(0)
-    if dist is not None:                   # the only collective of the path: episode statistics, once per iteration
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    stats = stats.cpu().tolist()
+    # the only collective of the path: episode statistics, all-reduced once per iteration (NCCL, side stream)
+    from gym_cellular_b200.distributed import StatsReducer
+    totals = StatsReducer().start(torch.stack([b["env"]._stats for b in batches]).sum(0)).result()
     alg_bytes = sum(b["bytes"] * b["n"] for b in batches)           # per step, per rank
     peak, peak_src = measured_peak()
     step_s = ms * 1e-3 / steps
@@ -340,8 +339,7 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes // len(batches),
                      "bytes_per_env_step": alg_bytes / n_rank, "kernels_per_step": len(batches),
                      "l2_resident": WORKLOADS[workload]["l2_resident"]},
-        "episode_stats": {"env_steps": stats[0], "unsafe_steps": stats[1], "count_sum": stats[2],
-                          "episodes_truncated": stats[3], "reward_sum": stats[4] / 2.0 ** 24},
+        "episode_stats": totals,
     }
     for b in batches:
         b["env"].close()

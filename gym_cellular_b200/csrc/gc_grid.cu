@@ -88,11 +88,9 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
                 }
                 if (trigger) {
                     if (RNG == GC_RNG_PHILOX) {
-                        uint32_t w[4];
-                        const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
-                        philox4x32_10(static_cast<uint32_t>(gid0) | e, static_cast<uint32_t>(gid0 >> 32), ctr, 1u,
-                                      io.round_key, w);
-                        b00 = w[0] >> 31; b10 = w[1] >> 31; k = w[2] >> 31;          // floor(u * 2)
+                        // given the trigger (word < p * 2^32) the low bits of the word are uniform up
+                        // to 2^-25: they serve as the three binary draws that matter (b00, b10, k)
+                        b00 = trig[e] & 1u; b10 = (trig[e] >> 1) & 1u; k = (trig[e] >> 2) & 1u;
                     }
                     // the drawn 2x2 bits (times tree_positions) replace jurisdiction k's trees: :162
                     const uint32_t T0 = byte_of(s0w, e) & 3u, T1 = byte_of(s1w, e) & 3u;

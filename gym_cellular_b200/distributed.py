@@ -1,0 +1,75 @@
+"""Multi-GPU sharding of the env batch: one process (rank) per GPU, no data-path collective.
+
+Env instances never interact (reference: no cross-env term anywhere in step(),
+cells3states3actions3.py:116-125), so a global batch is cut into contiguous global-id ranges and each
+rank steps its own `CellularVectorEnv` with `env_id_offset` = first global id.  Philox streams are
+keyed by GLOBAL env id, hence results are independent of the world size.  The only exchange is one
+all-reduce(SUM) of the int64 episode-statistics vector per rollout iteration (NCCL over
+NVLink/NVSwitch on GPUs; any torch.distributed backend works -- the CPU tests use gloo).
+"""
+import torch
+
+ALIGN = 16          # shard boundaries are multiples of the vector width of the kernels
+
+
+def shard_range(n_global, rank, world_size, align=ALIGN):
+    """-> (offset, count) of rank's contiguous slice; offsets are multiples of `align`, the slices
+    tile [0, n_global) exactly and differ by at most `align` envs in size."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank outside the world")
+    blocks = (n_global + align - 1) // align
+    lo = (blocks * rank // world_size) * align
+    hi = min((blocks * (rank + 1) // world_size) * align, n_global)
+    return lo, max(hi - lo, 0)
+
+
+def make_sharded_env(n_global, rank=None, world_size=None, **kwargs):
+    """This rank's shard of a global batch of `n_global` envs as a CellularVectorEnv."""
+    import torch.distributed as dist
+    from .vector_env import CellularVectorEnv
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    offset, count = shard_range(n_global, rank, world_size)
+    if count == 0:
+        raise ValueError(f"rank {rank} of {world_size} gets no envs out of {n_global}")
+    return CellularVectorEnv(num_envs=count, env_id_offset=offset, **kwargs)
+
+
+class StatsReducer:
+    """All-reduce of the episode statistics, issued once per iteration on a side stream so that it
+    overlaps the next steps (the vector is 64 bytes: pure latency)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self._stream = None
+        self._buf = None
+        self._work = None
+
+    def start(self, stats):
+        """Snapshot `stats` (int64 [N_STATS], any device) and start summing it over the ranks."""
+        import torch.distributed as dist
+        self._buf = stats.detach().clone()
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            self._work = None
+            return self
+        if self._buf.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=self._buf.device)
+            self._stream.wait_stream(torch.cuda.current_stream(self._buf.device))
+            with torch.cuda.stream(self._stream):
+                self._work = dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            self._work = dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return self
+
+    def result(self):
+        """Global totals as a dict (waits for the reduction)."""
+        if self._work is not None:
+            self._work.wait()
+            if self._buf.is_cuda:
+                torch.cuda.current_stream(self._buf.device).wait_stream(self._stream)
+        s = self._buf.cpu().tolist()
+        return {"env_steps": s[0], "unsafe_steps": s[1], "count_sum": s[2], "episodes_truncated": s[3],
+                "reward_sum": s[4] / 2.0 ** 24}

@@ -61,12 +61,13 @@ typedef struct {
  * and the uniform handed to the reference-style comparison is u = word * 2^-32 (exact).
  * Cellular family: draw slot c (cell c) uses word c of the env's own stream.
  * Grid world: the trigger draw of env g is word (g % 4) of the block shared by the four envs
- * g/4*4 .. g/4*4+3:  philox(key, ctr = ((g/4)_lo, (g/4)_hi, t, 0))[g % 4]  (one Philox block per
- * four env-steps); the five integers drawn when the trigger fires (b00, b01, b10, b11, k in
- * reference order) come from the env's own stream philox(key, ctr = (g_lo, g_hi, t, 1 + w/4))[w%4]
- * with w = 0, 3, 1, 4, 2 (b01 and b11 are multiplied by tree_positions == 0, so block 1 suffices).
+ * g/4*4 .. g/4*4+3:  w = philox(key, ctr = ((g/4)_lo, (g/4)_hi, t, 0))[g % 4]  (one Philox block per
+ * four env-steps), u = w * 2^-32.  When the trigger fires (w < p * 2^32) the binary draws that
+ * matter are taken from the low bits of the same word, which are uniform given the trigger up to
+ * 2^-25: b00 = bit 0, b10 = bit 1, k = bit 2 (b01 = bit 3, b11 = bit 4 are multiplied by
+ * tree_positions == 0 in the reference).
  */
-static const int GW_SLOT_WORD[6] = {-1, 0, 3, 1, 4, 2};
+static const int GW_SLOT_BIT[6] = {-1, 0, 3, 1, 4, 2};
 
 static void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
 {
@@ -107,14 +108,13 @@ static double draw_uniform(draw_src *d, int slot)
         return d->replay[slot];
     uint32_t key[2] = {(uint32_t)d->cfg->seed, (uint32_t)(d->cfg->seed >> 32)};
     if (d->cfg->kind == GCO_KIND_GRIDWORLD) {
-        if (slot == 0) {                                      /* trigger: block shared by 4 envs */
-            uint64_t grp = d->env_id >> 2;
-            uint32_t ctr[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), d->t, 0u};
-            uint32_t w[4];
-            philox4x32_10(ctr, key, w);
-            return (double)w[d->env_id & 3] * (1.0 / 4294967296.0);
-        }
-        slot = GW_SLOT_WORD[slot] + 4;                        /* own stream, blocks 1.. */
+        uint64_t grp = d->env_id >> 2;
+        uint32_t ctr[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), d->t, 0u};
+        uint32_t w[4];
+        philox4x32_10(ctr, key, w);
+        uint32_t word = w[d->env_id & 3];
+        if (slot == 0) return (double)word * (1.0 / 4294967296.0);              /* trigger */
+        return ((word >> GW_SLOT_BIT[slot]) & 1u) ? 0.75 : 0.25;                /* randint(2) = floor(u * 2) */
     }
     int blk = slot >> 2;
     if (blk != d->cached_block) {
