@@ -68,7 +68,7 @@ def load():
     L.gc_launch_count.restype = i64
     L.gc_reset.argtypes = [vp] * 6
     L.gc_step.argtypes = [vp, i64, i64] + [vp] * 13
-    L.gc_step_host.argtypes = [vp] * 19 + [i64]
+    L.gc_step_host.argtypes = [vp] * 21 + [i64]
     L.gc_poll_status.argtypes = [vp, vp]
     L.gc_encode.argtypes = [C.c_int, i64, i64, C.c_int32, C.c_int32, vp, vp, vp]
     L.gc_decode.argtypes = [C.c_int, i64, i64, C.c_int32, C.c_int32, vp, vp, vp]

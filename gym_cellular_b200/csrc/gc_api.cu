@@ -322,9 +322,10 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
 
 int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h_reward,
                  uint32_t *h_index, uint8_t *h_terminated, uint8_t *h_truncated, uint8_t *h_unsafe,
-                 uint8_t *h_count, int8_t *d_actions, int8_t *d_state, int32_t *d_t, float *d_reward,
-                 uint32_t *d_index, uint8_t *d_terminated, uint8_t *d_truncated, uint8_t *d_unsafe,
-                 uint8_t *d_count, int64_t *d_stats, int64_t chunk_envs)
+                 uint8_t *h_count, int8_t *h_se_row, int8_t *d_actions, int8_t *d_state, int32_t *d_t,
+                 float *d_reward, uint32_t *d_index, uint8_t *d_terminated, uint8_t *d_truncated,
+                 uint8_t *d_unsafe, uint8_t *d_count, int8_t *d_se_row, int64_t *d_stats,
+                 int64_t chunk_envs)
 {
     if (int rc = check_env(env)) return rc;
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
@@ -350,7 +351,7 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
         cudaStream_t st = env->hstream[k % kHostStreams];
         GC_CUDA(cudaMemcpy2DAsync(d_actions + b, ld, h_actions + b, ld, cnt_pad, C, cudaMemcpyHostToDevice, st));
         const StepIO io = make_io(env, b, cnt, d_actions, d_state, d_t, d_reward, d_index, d_terminated,
-                                  d_truncated, d_unsafe, d_count, nullptr, nullptr, d_stats);
+                                  d_truncated, d_unsafe, d_count, d_se_row, nullptr, d_stats);
         if (int rc = launch_step(env, io, st)) return rc;
         if (h_state) GC_CUDA(cudaMemcpy2DAsync(h_state + b, ld, d_state + b, ld, cnt, C, cudaMemcpyDeviceToHost, st));
         if (h_reward) GC_CUDA(cudaMemcpyAsync(h_reward + b, d_reward + b, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -359,6 +360,8 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
         if (h_truncated) GC_CUDA(cudaMemcpyAsync(h_truncated + b, d_truncated + b, cnt, cudaMemcpyDeviceToHost, st));
         if (h_unsafe) GC_CUDA(cudaMemcpyAsync(h_unsafe + b, d_unsafe + b, cnt, cudaMemcpyDeviceToHost, st));
         if (h_count) GC_CUDA(cudaMemcpyAsync(h_count + b, d_count + b, cnt, cudaMemcpyDeviceToHost, st));
+        if (h_se_row && d_se_row)
+            GC_CUDA(cudaMemcpy2DAsync(h_se_row + b, ld, d_se_row + b, ld, cnt, C, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < kHostStreams && i < k; ++i) GC_CUDA(cudaStreamSynchronize(env->hstream[i]));
     env->global_step += 1;

@@ -129,7 +129,7 @@ class _CellularEnv(gym.Env):
         obs, rew, term, trunc, infos = vec.step(a)
         self._state = tuple(int(o[0]) for o in obs)
         self.reward = float(rew[0])
-        self.side_effects = self._side_effects_matrix(vec._se_row[:, 0].cpu().numpy())
+        self.side_effects = self._side_effects_matrix(infos["side_effects"][:, 0])
         self.data['side_effects_incidence'] = 0.0
         for _ in range(int(infos["count"][0])):
             self.data['side_effects_incidence'] += 1.0 / self.n_cells
@@ -312,7 +312,7 @@ class GridWorldEnv(gym.Env):
         obs, rew, term, trunc, infos = vec.step(codes.astype(np.int8).reshape(2, 1))
         self._state = self.prior_knowledge.decellularize([int(o[0]) for o in obs], 'state')
         self.reward = float(rew[0])
-        self.side_effects = self._side_effects_matrix(vec._se_row[:, 0].cpu().numpy())
+        self.side_effects = self._side_effects_matrix(infos["side_effects"][:, 0])
         self.data['side_effects_incidence'] = int(infos["count"][0]) / N_JURISDICTIONS
         self.data['time_step'] += 1
         return self._state, self.reward, False, False, self.get_info()

@@ -156,6 +156,7 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         self.action_space = sp.Tuple(
             [sp.MultiDiscrete(np.full(self.num_envs, self.n_actions)) for _ in range(Cn)])
         self.closed = False
+        self._build_views()
         self.reset()
 
     # ------------------------------------------------------------------------------------------
@@ -251,8 +252,7 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             return self._step_host(actions)
         self._load_actions_device(actions)
         self.step_device(replay_u=replay_u)
-        return (self._obs_device(), self._reward[:self.num_envs], self._terminated[:self.num_envs].bool(),
-                self._truncated[:self.num_envs].bool(), self._infos_device())
+        return self._v_obs, self._v_reward, self._v_term, self._v_trunc, self._v_infos
 
     def step_device(self, actions=None, replay_u=None):
         """Launch one step on the current stream; no host synchronisation, no output marshalling.
@@ -321,17 +321,33 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if actions.data_ptr() != self._actions.data_ptr():
             self._actions[:, :self.num_envs].copy_(actions.to(self.device, non_blocking=True))
 
+    def _build_views(self):
+        """Zero-copy views handed back by step()/reset(): they alias the env's buffers (valid until the
+        next step) and are built once, so a device-path step() launches exactly one kernel."""
+        n = self.num_envs
+        self._v_obs = tuple(self._state[c, :n] for c in range(self.n_cells))
+        self._v_reward = self._reward[:n]
+        self._v_term = self._terminated[:n].view(torch.bool)
+        self._v_trunc = self._truncated[:n].view(torch.bool)
+        self._v_infos = {"unsafe": self._unsafe[:n].view(torch.bool), "count": self._count[:n],
+                         "time_step": self._t[:n]}
+        # the index is a uint32 payload in an int32 tensor: directly usable whenever it fits 31 bits
+        key = "tabular_state" if self.n_states ** self.n_cells <= 2 ** 31 else "tabular_state_u32"
+        self._v_infos[key] = self._index[:n]
+        if self._se_row is not None:
+            self._v_infos["side_effects"] = self._se_row[:, :n]
+
     def _obs_device(self):
-        return tuple(self._state[c, :self.num_envs] for c in range(self.n_cells))
+        return self._v_obs
 
     def _infos_device(self):
-        n = self.num_envs
-        infos = {"unsafe": self._unsafe[:n].bool(), "count": self._count[:n],
-                 "side_effects_incidence": self._count[:n].to(torch.float32) / self.n_cells,
-                 "tabular_state": self.tabular_state(), "time_step": self._t[:n]}
-        if self._se_row is not None:
-            infos["side_effects"] = self._se_row[:, :n]
-        return infos
+        """`tabular_state` is the int32 index tensor (zero-copy); for spaces above 2^31 states the key
+        is `tabular_state_u32` (raw uint32 payload) and `tabular_state()` widens it to int64."""
+        return self._v_infos
+
+    def side_effects_incidence(self):
+        """count / n_cells, as the reference's data['side_effects_incidence'] (float32 tensor)."""
+        return self._count[:self.num_envs].to(torch.float32) / self.n_cells
 
     def _alloc_host(self):
         ld, Cn = self.ld, self.n_cells
@@ -340,6 +356,8 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                       "reward": pin(ld, dtype=torch.float32), "index": pin(ld, dtype=torch.int32),
                       "terminated": pin(ld, dtype=torch.uint8), "truncated": pin(ld, dtype=torch.uint8),
                       "unsafe": pin(ld, dtype=torch.uint8), "count": pin(ld, dtype=torch.uint8)}
+        if self._se_row is not None:
+            self._host["se_row"] = pin(Cn, ld, dtype=torch.int8)
         self._host_np = {k: v.numpy() for k, v in self._host.items()}
 
     @property
@@ -371,13 +389,16 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         H = self._host
         _lib.check(self._lib.gc_step_host(
             self._h, h_actions_ptr, _ptr(H["state"]), _ptr(H["reward"]), _ptr(H["index"]),
-            _ptr(H["terminated"]), _ptr(H["truncated"]), _ptr(H["unsafe"]), _ptr(H["count"]),
+            _ptr(H["terminated"]), _ptr(H["truncated"]), _ptr(H["unsafe"]), _ptr(H["count"]), _ptr(H.get("se_row")),
             _ptr(self._actions), _ptr(self._state), _ptr(self._t), _ptr(self._reward), _ptr(self._index),
             _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
-            _ptr(self._stats), self.host_chunk_envs))
+            _ptr(self._se_row), _ptr(self._stats), self.host_chunk_envs))
         obs = tuple(h["state"][c, :n] for c in range(self.n_cells))
         infos = {"unsafe": h["unsafe"][:n].view(np.bool_), "count": h["count"][:n],
+                 "side_effects_incidence": h["count"][:n].astype(np.float32) / self.n_cells,
                  "tabular_state": h["index"][:n].view(np.uint32)}
+        if "se_row" in h:
+            infos["side_effects"] = h["se_row"][:, :n]
         return obs, h["reward"][:n], h["terminated"][:n].view(np.bool_), h["truncated"][:n].view(np.bool_), infos
 
 

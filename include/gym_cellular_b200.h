@@ -164,12 +164,14 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
 /* The same step for a HOST caller: h_* are host buffers (pinned for full speed) in the same
  * layouts with row stride ld; d_* the caller-owned resident device arrays.  Copies the actions in,
  * steps, copies state/reward/index/flags out, pipelined over chunks on the handle's own streams;
- * returns after everything has landed in the host buffers.  Any h_* output may be NULL. */
+ * returns after everything has landed in the host buffers.  Any h_* output may be NULL; the row-0
+ * side-effect codes are produced only when d_se_row is given (and copied out when h_se_row is). */
 int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h_reward,
                  uint32_t *h_index, uint8_t *h_terminated, uint8_t *h_truncated, uint8_t *h_unsafe,
-                 uint8_t *h_count, int8_t *d_actions, int8_t *d_state, int32_t *d_t, float *d_reward,
-                 uint32_t *d_index, uint8_t *d_terminated, uint8_t *d_truncated, uint8_t *d_unsafe,
-                 uint8_t *d_count, int64_t *d_stats, int64_t chunk_envs);
+                 uint8_t *h_count, int8_t *h_se_row, int8_t *d_actions, int8_t *d_state, int32_t *d_t,
+                 float *d_reward, uint32_t *d_index, uint8_t *d_terminated, uint8_t *d_truncated,
+                 uint8_t *d_unsafe, uint8_t *d_count, int8_t *d_se_row, int64_t *d_stats,
+                 int64_t chunk_envs);
 
 /* Reads and clears the handle's device status word (synchronises `stream`).  Returns GC_OK or
  * GC_ERR_ACTION if some env received a grid-world action without any go-to position since the

@@ -65,12 +65,12 @@ def test_polarisation_exhaustive_vs_reference(B, golden_pol, tag, C, difficulty,
     env.set_state(detab(pairs // n_s, C, 3))
     obs, rew, term, trunc, info = env.step(dev(detab(pairs % n_s, C, 3)))
     assert (host(torch.stack(obs)).T == g[f"{tag}_next"]).all()
-    assert (host(info["tabular_state"]) == g[f"{tag}_next_tab"]).all()
+    assert (host(env.tabular_state()) == g[f"{tag}_next_tab"]).all()
     np.testing.assert_allclose(host(rew), g[f"{tag}_reward_{reward}"], rtol=REWARD_RTOL, atol=REWARD_ATOL)
     se = g[f"{tag}_se_{difficulty}"]
     assert (host(info["side_effects"]).T == se[:, 0, :]).all()
     assert (host(info["unsafe"]) == (se == 2).any(axis=(1, 2))).all()
-    np.testing.assert_allclose(host(info["side_effects_incidence"]), g[f"{tag}_incidence"], rtol=1e-6)
+    np.testing.assert_allclose(host(env.side_effects_incidence()), g[f"{tag}_incidence"], rtol=1e-6)
     assert not host(term).any() and not host(trunc).any() and (host(info["time_step"]) == 1).all()
 
 
@@ -124,7 +124,7 @@ def test_gridworld_exhaustive_vs_reference(B, golden_gw):
     env.set_state(s.T.copy())
     obs, rew, term, trunc, info = env.step(dev(a.T), replay_u=_gw_replay(g["gw_case_u0"], g["gw_case_bits"], g["gw_case_k"]))
     assert (host(env.state).T == g["gw_case_next"]).all()
-    assert (host(info["tabular_state"]) == g["gw_case_tab"]).all()
+    assert (host(env.tabular_state()) == g["gw_case_tab"]).all()
     assert (host(rew) == g["gw_case_reward"]).all()
     assert (host(info["count"]) / 2 == g["gw_case_incidence"]).all()
     assert (host(info["side_effects"]).T == g["gw_case_se"][:, 0, :]).all() and not host(info["unsafe"]).any()
@@ -134,7 +134,7 @@ def test_gridworld_exhaustive_vs_reference(B, golden_gw):
     env = B.CellularVectorEnv(kind="gridworld", num_envs=len(s))
     env.set_state(s.T.copy())
     _, rew, _, _, info = env.step(dev(a.T), replay_u=np.zeros((len(s), 6)))
-    assert (host(env.state).T == g["gw_barren_next"]).all() and (host(info["tabular_state"]) == g["gw_barren_tab"]).all()
+    assert (host(env.state).T == g["gw_barren_next"]).all() and (host(env.tabular_state()) == g["gw_barren_tab"]).all()
     assert (host(rew) == g["gw_barren_reward"]).all() and (host(info["count"]) == 2).all()
 
 
