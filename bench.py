@@ -192,6 +192,42 @@ def time_device_path(batches, steps, warmup, dist, device, sampler_index):
     return ms, launches, clk.summary()
 
 
+def time_graph_path(batches, steps, device):
+    """Launch-bound batch sizes: RING captured steps per CUDA graph, replayed steps/RING times."""
+    import torch
+    graphs = [b["env"].capture_steps(b["ring"]) for b in batches]
+    reps = max(1, steps // RING)
+    for g in graphs:
+        g.replay()
+    torch.cuda.synchronize(device)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(reps):
+        for g in graphs:
+            g.replay()
+    stop.record()
+    stop.synchronize()
+    return start.elapsed_time(stop), reps * RING
+
+
+def measure_pcie(device, nbytes=1 << 28):
+    """Pinned-memory copy bandwidth of this box (GB/s), for reading the e2e figure: the host path
+    moves (C) bytes in and (C + 12) bytes out per env-step and is bound by these two numbers."""
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    out = {}
+    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(device)
+        out[name] = round(3 * nbytes / (time.perf_counter() - t0) / 1e9, 1)
+    return out
+
+
 def time_host_path(batches, steps, warmup, dist, device):
     """End to end through the host-facing call: pinned numpy actions in, numpy results out."""
     import torch
@@ -319,6 +355,11 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
     batches = build_batches(workload, device, rank)
     n_rank = sum(b["n"] for b in batches)
     ms, launches, clocks = time_device_path(batches, steps, warmup, dist, device, device.index)
+    graph_res = None
+    if WORKLOADS[workload]["l2_resident"] and dist is None:
+        g_ms, g_steps = time_graph_path(batches, steps, device)
+        graph_res = {"value": n_rank * g_steps / (g_ms * 1e-3), "ms_per_step": g_ms / g_steps,
+                     "steps_per_graph": RING}
     el_host, h2d, d2h = time_host_path(batches, e2e_steps, 2, dist, device)
     # the only collective of the path: episode statistics, all-reduced once per iteration (NCCL, side stream)
     from gym_cellular_b200.distributed import StatsReducer
@@ -340,6 +381,7 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
                      "bytes_per_env_step": alg_bytes / n_rank, "kernels_per_step": len(batches),
                      "l2_resident": WORKLOADS[workload]["l2_resident"]},
         "episode_stats": totals,
+        "cuda_graph": graph_res,
     }
     for b in batches:
         b["env"].close()
@@ -390,7 +432,7 @@ def main():
                 extra[w] = {"description": WORKLOADS[w]["desc"], "value": r["value"], "ms_per_step": r["ms_per_step"],
                             "roofline_frac": r["roofline"]["frac"], "achieved_gbs": r["roofline"]["achieved"],
                             "l2_resident": WORKLOADS[w]["l2_resident"], "e2e": r["e2e"]["value"],
-                            "kernels_per_step": r["roofline"]["kernels_per_step"]}
+                            "kernels_per_step": r["roofline"]["kernels_per_step"], "cuda_graph": r["cuda_graph"]}
     if rank == 0:
         line = {
             "metric": "env-steps/sec", "value": main_res["value"], "unit": "env-steps/s", "n_gpus": world,
@@ -403,7 +445,8 @@ def main():
                        "l2": "per-step working set larger than L2" if not WORKLOADS[args.workload]["l2_resident"]
                              else "working set is L2-resident (launch-bound, not an HBM measurement)",
                        "actions": f"ring of {RING} pre-generated device buffers, uniform random"},
-            "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
+            "e2e": {**main_res["e2e"], "pcie_measured": measure_pcie(device)},
+            "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
             "roofline": main_res["roofline"], "episode_stats": main_res["episode_stats"],
         }
         if extra:

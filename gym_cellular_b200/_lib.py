@@ -17,7 +17,7 @@ STAT_STEPS, STAT_UNSAFE, STAT_COUNT, STAT_TRUNCATED, STAT_REWARD_Q24 = range(5)
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_ACTION = 0, -1, -2, -3, -4
 
 EXPORTS = ["gc_abi_version", "gc_last_error", "gc_create", "gc_destroy", "gc_set_tables",
-           "gc_set_global_step", "gc_get_global_step", "gc_launch_count", "gc_reset", "gc_step",
+           "gc_set_global_step", "gc_get_global_step", "gc_sync_global_step", "gc_launch_count", "gc_reset", "gc_step",
            "gc_step_host", "gc_poll_status", "gc_encode", "gc_decode"]
 
 
@@ -64,6 +64,7 @@ def load():
     L.gc_set_global_step.argtypes = [vp, i64]
     L.gc_get_global_step.argtypes = [vp]
     L.gc_get_global_step.restype = i64
+    L.gc_sync_global_step.argtypes = [vp, vp]
     L.gc_launch_count.argtypes = [vp]
     L.gc_launch_count.restype = i64
     L.gc_reset.argtypes = [vp] * 6

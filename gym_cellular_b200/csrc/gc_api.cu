@@ -49,7 +49,9 @@ struct gc_env {
     int n_sm;
     int64_t global_step;
     int64_t launches;
-    unsigned long long *d_status;
+    unsigned long long *d_status;   // [0] status bits; the same allocation holds the step words:
+    uint32_t *d_step;               // device-resident global step (RNG counter of non-episodic envs)
+    uint32_t *d_done;               // block-arrival counter of the step kernels
     uint2 *d_pair_lut;            // fast-path table (GC_PAIR_LUT_ENTRIES), device memory owned by the handle
     bool fast_ok;
     cudaStream_t hstream[kHostStreams];
@@ -97,6 +99,8 @@ StepIO make_io(const gc_env *env, int64_t begin, int64_t count, const int8_t *ac
         io.round_key[2 * r + 1] = io.seed_hi + static_cast<uint32_t>(r) * 0xBB67AE85u;
     }
     io.rng_counter = static_cast<uint32_t>(env->global_step);
+    io.step_ctr = nullptr;
+    io.done_ctr = nullptr;
     io.episodic = (env->cfg.flags & GC_F_RNG_EPISODIC) ? 1 : 0;
     io.max_episode_steps = env->cfg.max_episode_steps;
     return io;
@@ -167,8 +171,12 @@ int gc_create(const gc_config *cfg, gc_env **out)
     env->grid.dispersal_thr_m1 = env->grid.dispersal_thr_nz ? static_cast<uint32_t>(env->grid.dispersal_thr - 1ull) : 0u;
     env->grid.dispersal_prob = cfg->dispersal_prob;
     env->tables_set = (cfg->kind == GC_KIND_GRIDWORLD);
-    cudaError_t e = cudaMalloc(&env->d_status, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(env->d_status, 0, sizeof(unsigned long long));
+    cudaError_t e = cudaMalloc(&env->d_status, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(env->d_status, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        env->d_step = reinterpret_cast<uint32_t *>(env->d_status + 1);
+        env->d_done = env->d_step + 1;
+    }
     if (e == cudaSuccess && cfg->kind == GC_KIND_GRIDWORLD) {
         static uint32_t lut[GC_GRID_LUT_ENTRIES];
         gc_build_grid_lut(lut);
@@ -272,10 +280,26 @@ int gc_set_global_step(gc_env *env, int64_t step)
 {
     if (int rc = check_env(env)) return rc;
     env->global_step = step;
+    const uint32_t v = static_cast<uint32_t>(step);
+    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_CUDA(cudaMemcpy(env->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));   // synchronous: rare, control path
     return GC_OK;
 }
 
+// Host mirror of the step counter.  Replaying a captured CUDA graph advances only the device word;
+// gc_sync_global_step reads it back.
 int64_t gc_get_global_step(const gc_env *env) { return env ? env->global_step : -1; }
+
+int gc_sync_global_step(gc_env *env, void *stream)
+{
+    if (int rc = check_env(env)) return rc;
+    GC_CUDA(cudaSetDevice(env->cfg.device));
+    uint32_t v = 0;
+    GC_CUDA(cudaMemcpyAsync(&v, env->d_step, sizeof(v), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    GC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    env->global_step = (env->global_step & ~0xFFFFFFFFll) | v;
+    return GC_OK;
+}
 
 int64_t gc_launch_count(const gc_env *env) { return env ? env->launches : -1; }
 
@@ -313,10 +337,21 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
         return fail(GC_ERR_INVALID, "a required device pointer is NULL");
     if (int rc = check_range(env, env_begin, env_count)) return rc;
     GC_CUDA(cudaSetDevice(env->cfg.device));
-    const StepIO io = make_io(env, env_begin, env_count, actions, state, t, reward, index, terminated,
-                              truncated, unsafe, count, se_row, replay_u, stats);
+    StepIO io = make_io(env, env_begin, env_count, actions, state, t, reward, index, terminated,
+                        truncated, unsafe, count, se_row, replay_u, stats);
+    const bool full = env_begin == 0 && env_count == env->cfg.n_envs;
+    if (full) {                              // whole shard in one launch: device-resident step counter,
+        io.step_ctr = env->d_step;           // advanced by the kernel itself (survives graph replay)
+        io.done_ctr = env->d_done;
+    }
     if (int rc = launch_step(env, io, static_cast<cudaStream_t>(stream))) return rc;
-    if (env_begin + env_count == env->cfg.n_envs) env->global_step += 1;   // a full pass over the shard
+    if (full) {
+        env->global_step += 1;
+    } else if (env_begin + env_count == env->cfg.n_envs) {                 // last chunk of a chunked pass
+        env->global_step += 1;
+        const uint32_t v = static_cast<uint32_t>(env->global_step);
+        GC_CUDA(cudaMemcpyAsync(env->d_step, &v, sizeof(v), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    }
     return GC_OK;
 }
 
@@ -365,6 +400,10 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
     }
     for (int i = 0; i < kHostStreams && i < k; ++i) GC_CUDA(cudaStreamSynchronize(env->hstream[i]));
     env->global_step += 1;
+    {
+        const uint32_t v = static_cast<uint32_t>(env->global_step);
+        GC_CUDA(cudaMemcpy(env->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));
+    }
     return GC_OK;
 }
 

@@ -47,7 +47,7 @@ struct EnvAcc {
 template <int N, int C, int RNG, bool WITH_SE, bool FIRST>
 __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io, const uint2 *s_pair,
                                          const uint2 *s_single, const uint8_t (*s_se)[GC_TBL], int c0,
-                                         int64_t e0, int rem, uint32_t gid_lo, uint32_t gid_hi,
+                                         int64_t e0, int rem, uint32_t gid_lo, uint32_t gid_hi, uint32_t step_counter,
                                          const int (&tin)[kEPT], uint32_t keep, const uint32_t (&sw)[4],
                                          const uint32_t (&aw)[4], EnvAcc &acc)
 {
@@ -55,7 +55,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
     if (RNG == GC_RNG_PHILOX) {
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
-            const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+            const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
             philox4x32_10(gid_lo | e, gid_hi, ctr, static_cast<uint32_t>(c0 >> 2), io.round_key, rnd[e]);
         }
     }
@@ -160,6 +160,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
+    const uint32_t step_counter = launch_step_counter(io);
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;   // < 2^32 per thread and launch
     long long st_reward = 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
@@ -187,19 +188,19 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.add[e] = 0; acc.orr[e] = 0; acc.first[e] = 0; acc.idx[e] = 0; }
 
         if (NG == 0) {
-            do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, tin, keep, sa, aa, acc);
+            do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
         } else {
-            do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, tin, keep, sa, aa, acc);
+            do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
 #pragma unroll 1
             for (int g = 1; g < NG; ++g) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { sa[i] = sb[i]; aa[i] = ab[i]; }
                 if (g + 1 < NG) load_cells<4>(io, 4 * (g + 1), e0, sb, ab);
                 else if (R > 0) load_cells<R>(io, 4 * NG, e0, sb, ab);
-                do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, tin, keep, sa, aa, acc);
+                do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
             }
             if (R > 0)
-                do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, tin, keep, sb, ab, acc);
+                do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sb, ab, acc);
         }
 
         uint32_t unsafe_w = 0, count_w = 0;
@@ -236,6 +237,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         const ThreadStats ts = {st_steps, st_unsafe, st_count, st_trunc, st_reward};
         block_flush_stats(ts, s_stats, io.stats);
     }
+    tick_step_counter(io);
 }
 
 template <int C, int RNG>

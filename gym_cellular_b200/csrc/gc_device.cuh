@@ -47,6 +47,33 @@ struct ThreadStats {
     long long reward_q24;
 };
 
+// Global step of the launch: device-resident when the launch covers the whole shard (so that a captured
+// CUDA graph advances its RNG counter on every replay), else the value the host passed.
+__device__ __forceinline__ uint32_t launch_step_counter(const StepIO &io)
+{
+    // (not a ?: of a volatile and a plain lvalue: that makes the parameter read itself volatile and
+    // sends it through a generic-address load of the kernel parameter block)
+    uint32_t v = io.rng_counter;
+    if (io.step_ctr != nullptr) v = *reinterpret_cast<const volatile uint32_t *>(io.step_ctr);
+    return v;
+}
+
+// Called by every thread at kernel exit: the last block to arrive advances the device step counter.
+// Every thread read the counter at kernel entry, before its block's arrival, so no block can observe
+// the incremented value within the same launch.
+__device__ __forceinline__ void tick_step_counter(const StepIO &io)
+{
+    if (io.step_ctr == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t arrived = atomicAdd(io.done_ctr, 1u);
+        if (arrived == gridDim.x - 1) {
+            *io.done_ctr = 0u;
+            *const_cast<uint32_t *>(io.step_ctr) = *reinterpret_cast<const volatile uint32_t *>(io.step_ctr) + 1u;
+        }
+    }
+}
+
 // byte mask of the envs of a 4-env word that lie inside the launch range (rem = envs left, >= 1)
 __device__ __forceinline__ uint32_t valid_bytes(int rem) { return rem >= 4 ? 0xFFFFFFFFu : ((1u << (8 * rem)) - 1u); }
 

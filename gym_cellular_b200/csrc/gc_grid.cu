@@ -26,6 +26,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
+    const uint32_t step_counter = launch_step_counter(io);
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     const int64_t ld = io.ld;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
@@ -58,7 +59,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             const uint64_t grp = gid0 >> 2;
             const bool same_t = !io.episodic || (tin[0] == tin[1] && tin[1] == tin[2] && tin[2] == tin[3]);
             if (same_t) {
-                const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[0]) : io.rng_counter;
+                const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[0]) : step_counter;
                 philox4x32_10(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32), ctr, 0u, io.round_key, trig);
             } else {
 #pragma unroll 1
@@ -153,6 +154,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         const ThreadStats ts = {st_steps, 0, st_count, st_trunc, static_cast<long long>(st_reward) << 24};
         block_flush_stats(ts, s_stats, io.stats);
     }
+    tick_step_counter(io);
 }
 
 }  // namespace

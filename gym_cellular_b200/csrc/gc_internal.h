@@ -28,7 +28,9 @@ struct StepIO {
     int64_t env_id_offset;
     uint32_t seed_lo, seed_hi;
     uint32_t round_key[20];     // Philox round keys (k0_r, k1_r), r = 0..9: warp-uniform, precomputed on the host
-    uint32_t rng_counter;       // global step (ignored when episodic)
+    uint32_t rng_counter;       // global step (ignored when episodic); used when step_ctr == NULL
+    const uint32_t *step_ctr;   // device-resident global step: read by every thread at kernel entry and
+    uint32_t *done_ctr;         // advanced by the last block to finish (CUDA-graph friendly), or NULL
     int32_t  episodic;
     int32_t  max_episode_steps;
 };

@@ -37,6 +37,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
+    const uint32_t step_counter = launch_step_counter(io);
     ThreadStats ts = {0, 0, 0, 0, 0};
     const int64_t ld = io.ld;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
@@ -74,7 +75,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                 if (RNG == GC_RNG_PHILOX) {
                     if ((c & 3) == 0) {
                         const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
-                        const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : io.rng_counter;
+                        const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
                         philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr,
                                       static_cast<uint32_t>(c >> 2), io.round_key, rnd);
                     }
@@ -135,6 +136,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         st_stream_u32(io.count + e0, count_w);
     }
     if (io.stats) block_flush_stats(ts, s_stats, io.stats);
+    tick_step_counter(io);
 }
 
 // ---------------------------------------------------------------------------------------------

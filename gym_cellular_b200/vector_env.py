@@ -290,6 +290,26 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                 check(rc)
         return launch
 
+    def capture_steps(self, action_ring):
+        """Captures one step per tensor of `action_ring` (int8 [n_cells, ld] device tensors, kept alive
+        by the caller) into a CUDA graph and returns it; `graph.replay()` then runs len(action_ring)
+        steps with a single launch.  The RNG step counter lives in device memory and is advanced by the
+        kernels themselves, so every replay draws fresh numbers.  For launch-bound batch sizes."""
+        calls = [self.bind_step(a) for a in action_ring]
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(graph):
+            for call in calls:
+                call()
+        self._graph_dirty = True            # host mirror of the step counter is refreshed on demand
+        return graph
+
+    def sync_step_counter(self):
+        """Refreshes the host mirror of the global step after CUDA-graph replays; returns it."""
+        _lib.check(self._lib.gc_sync_global_step(self._h, self._stream()))
+        self._graph_dirty = False
+        return int(self._lib.gc_get_global_step(self._h))
+
     @property
     def action_buffer(self):
         """int8 [n_cells, num_envs] device view: write actions here and call step_device()."""
@@ -385,6 +405,8 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             h["actions"][:, :n] = actions.T
         else:
             raise ValueError(f"actions must have shape {(self.n_cells, n)} or {(n, self.n_cells)}")
+        if getattr(self, "_graph_dirty", False):
+            self.sync_step_counter()
         torch.cuda.current_stream(self.device).synchronize()     # resident state must be settled
         H = self._host
         _lib.check(self._lib.gc_step_host(

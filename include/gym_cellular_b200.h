@@ -126,9 +126,13 @@ int gc_create(const gc_config *cfg, gc_env **out);
 int gc_destroy(gc_env *env);
 int gc_set_tables(gc_env *env, const gc_cell_tables *tables);   /* cellular family only */
 
-/* Global step counter used as the RNG counter when GC_F_RNG_EPISODIC is off; gc_step increments it. */
+/* Global step counter used as the RNG counter when GC_F_RNG_EPISODIC is off.  It lives in device
+ * memory: a gc_step over the whole shard reads it in the kernel and the kernel advances it, so a
+ * gc_step captured into a CUDA graph keeps drawing fresh numbers on every replay.  The host keeps a
+ * mirror (gc_get_global_step); after graph replays call gc_sync_global_step to refresh it. */
 int gc_set_global_step(gc_env *env, int64_t step);
 int64_t gc_get_global_step(const gc_env *env);
+int gc_sync_global_step(gc_env *env, void *stream);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t gc_launch_count(const gc_env *env);
 

@@ -289,6 +289,37 @@ def test_host_path_equals_device_path(B, O):
         assert (np.stack(obs) == gwo.state).all() and (info["tabular_state"] == gwo.index).all() and (rew == gwo.reward).all()
 
 
+def test_cuda_graph_replay_advances_rng(B, O):
+    """A graph of 8 captured steps replayed 3 times = 24 distinct steps: the global-step RNG counter
+    lives on the device and is advanced by the kernels, so replays do not repeat their draws."""
+    n = 50000
+    rng = np.random.default_rng(3)
+    acts = np.full((8, 2, n), 4, np.int8)
+    for k in range(8):
+        acts[k, rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=17, dispersal_prob=0.2, max_episode_steps=10)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=17, dispersal_prob=0.2, max_episode_steps=10)
+    ring = []
+    for k in range(8):
+        a = torch.zeros(2, env.ld, dtype=torch.int8, device="cuda")
+        a[:, :n] = dev(acts[k])
+        ring.append(a)
+    graph = env.capture_steps(ring)
+    for rep in range(3):
+        graph.replay()
+        for k in range(8):
+            ora.step(acts[k])
+        assert_matches_oracle(env, ora, check_se=True)
+    assert env.sync_step_counter() == 24
+    env.step_device(dev(acts[0]))                       # ordinary launches continue from the same counter
+    ora.step(acts[0])
+    assert_matches_oracle(env, ora)
+    obs, rew, term, trunc, info = env.step(acts[1])     # and so does the host path
+    ora.step(acts[1])
+    assert (np.stack(obs) == ora.state).all() and (rew == ora.reward).all()
+    assert env.stats()["env_steps"] == 26 * n
+
+
 def test_shard_invariance(B):
     """Results for env i do not depend on which shard owns it (Philox keyed by global env id)."""
     n, T = 40000, 12
