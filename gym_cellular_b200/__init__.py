@@ -10,7 +10,8 @@ from .vector_env import CellularVectorEnv, make_vector_env
 from .codec import (generalized_cellular2tabular, generalized_tabular2cellular, cellular2tabular,
                     tabular2cellular)
 from .envs import (Cells3States3Actions3Env, Cells2Rest3Env, Cells3ResetVDeadlockEnv, GridWorldEnv,
-                   PriorKnowledge, GridWorldPriorKnowledge)
+                   DebugEnv, DeepPlanningDebugEnv, DeepExplorationDebugEnv, PriorKnowledge,
+                   GridWorldPriorKnowledge)
 from . import registration  # noqa: F401  (registers the gym_cellular/<Name>-v0 ids)
 
 __all__ = ["CellularVectorEnv", "make_vector_env", "tables", "right_polarizing", "multiple_optima",

@@ -32,7 +32,7 @@ class GcConfig(C.Structure):
 class GcCellTables(C.Structure):
     _fields_ = [("move", C.c_void_p), ("noisy", C.c_void_p), ("draws", C.c_void_p),
                 ("reward", C.c_void_p), ("side_effects", C.c_void_p), ("counted", C.c_void_p),
-                ("initial_state", C.c_void_p)]
+                ("initial_state", C.c_void_p), ("reward_noisy", C.c_void_p)]
 
 
 class GcError(RuntimeError):

@@ -231,6 +231,7 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
                 return fail(GC_ERR_INVALID, "move/noisy[%d][%d] outside [0, %d)", s, a, S);
             tab.sa[s * GC_LVL_PAD + a] = (uint32_t)mv | ((uint32_t)nz << 4) | ((uint32_t)dr << 8);
             tab.reward[s * GC_LVL_PAD + a] = t->reward[s * A + a];
+            tab.reward_noisy[s * GC_LVL_PAD + a] = (t->reward_noisy ? t->reward_noisy : t->reward)[s * A + a];
         }
     for (int j = 0; j < C; ++j)
         for (int s0 = 0; s0 < S; ++s0)

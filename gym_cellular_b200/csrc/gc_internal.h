@@ -40,6 +40,7 @@ struct StepIO {
 struct CellTables {
     uint32_t sa[GC_TBL];             // bits 0-3 move, 4-7 noisy, 8 draws
     float    reward[GC_TBL];
+    float    reward_noisy[GC_TBL];   // reward when the draw fired (== reward unless it depends on the next level)
     uint8_t  se[GC_MAX_CELLS][GC_TBL]; // [j][s0' * GC_LVL_PAD + s'_p]
     uint32_t place[GC_MAX_CELLS];    // mixed-radix place values S^c (mod 2^32)
     uint32_t place4[4];              // S^0..S^3: digits of four cells folded into one byte (fast path)

@@ -27,11 +27,12 @@ __global__ void __launch_bounds__(kThreads)
 cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ StepIO io)
 {
     __shared__ uint2 s_sa[GC_TBL];                 // .x packed move/noisy/draws, .y reward bits
+    __shared__ float s_rn[GC_TBL];                 // reward when the draw fired
     __shared__ uint8_t s_se[C][GC_TBL];
     __shared__ unsigned long long s_stats[5];
 
     for (int i = threadIdx.x; i < GC_TBL; i += kThreads)
-        s_sa[i] = make_uint2(tab.sa[i], __float_as_uint(tab.reward[i]));
+        s_sa[i] = make_uint2(tab.sa[i], __float_as_uint(tab.reward[i])), s_rn[i] = tab.reward_noisy[i];
     for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads)
         s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
@@ -69,9 +70,10 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const uint32_t s = byte_of(sw[c], e), a = byte_of(aw[c], e);
-                const uint2 ent = s_sa[(s * GC_LVL_PAD + a) & (GC_TBL - 1)];
-                r += __uint_as_float(ent.y);                       // left to right, from 0.0
+                const uint32_t sa_ix = (s * GC_LVL_PAD + a) & (GC_TBL - 1);
+                const uint2 ent = s_sa[sa_ix];
                 uint32_t nxt = ent.x & 15u;
+                bool fire = false;
                 if (RNG == GC_RNG_PHILOX) {
                     if ((c & 3) == 0) {
                         const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
@@ -79,13 +81,12 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                         philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr,
                                       static_cast<uint32_t>(c >> 2), io.round_key, rnd);
                     }
-                    const bool fire = (ent.x & 0x100u) && (static_cast<unsigned long long>(rnd[c & 3]) < tab.noise_thr);
-                    nxt = fire ? ((ent.x >> 4) & 15u) : nxt;
+                    fire = (ent.x & 0x100u) && (static_cast<unsigned long long>(rnd[c & 3]) < tab.noise_thr);
                 } else if (RNG == GC_RNG_REPLAY) {
-                    bool fire = false;
                     if (valid && (ent.x & 0x100u)) fire = io.replay[(e0 + e) * C + c] < tab.noise_prob;
-                    nxt = fire ? ((ent.x >> 4) & 15u) : nxt;
                 }
+                if (fire) nxt = (ent.x >> 4) & 15u;
+                r += fire ? s_rn[sa_ix] : __uint_as_float(ent.y);             // left to right, from 0.0
                 ns[c] = nxt;
             }
             if (tab.reward_log2) r = log1pf(r) * 1.44269504088896341f;

@@ -65,7 +65,11 @@ void gc_build_pair_lut(const gc_cell_tables *t, int C, int S, int A, bool noise,
         if (noise && fire && t->draws[s * A + a]) return (int)t->noisy[s * A + a];
         return (int)t->move[s * A + a];
     };
-    auto rw = [&](int s, int a) { return ok(s, a) ? (double)t->reward[s * A + a] : 0.0; };
+    auto rw = [&](int s, int a, int fire) {
+        if (!ok(s, a)) return 0.0;
+        if (noise && fire && t->draws[s * A + a] && t->reward_noisy) return (double)t->reward_noisy[s * A + a];
+        return (double)t->reward[s * A + a];
+    };
     auto se = [&](int j, int s0, int sp) { return (int)t->side_effects[((size_t)j * S + s0) * S + sp]; };
     auto cn = [&](int n) { return t->counted[n] ? 1u : 0u; };
     for (int p = 0; p < GC_PAIR_LUT_PAIRS; ++p) {
@@ -74,14 +78,14 @@ void gc_build_pair_lut(const gc_cell_tables *t, int C, int S, int A, bool noise,
         const uint32_t uns01 = (C >= 2 && (se(0, nc, nd) == 2 || se(1, nc, nd) == 2)) ? 1u : 0u;
         lut[p].x = (cn(nc) + cn(nd)) | (((1u << nc) | (1u << nd)) << 8) | (uns01 << 12) |
                    ((uint32_t)nc << 16) | ((uint32_t)nd << 24);
-        const float f = (float)(rw(sc, ac) + rw(sd, ad));
+        const float f = (float)(rw(sc, ac, (p >> 8) & 1) + rw(sd, ad, (p >> 9) & 1));
         std::memcpy(&lut[p].y, &f, sizeof(f));
     }
     for (int p = 0; p < 32; ++p) {
         const int s = p & 3, a = (p >> 2) & 3, n = nxt(s, a, (p >> 4) & 1);
         const uint32_t uns0 = (C == 1 && se(0, n, n) == 2) ? 1u : 0u;
         lut[GC_PAIR_LUT_PAIRS + p].x = cn(n) | ((1u << n) << 8) | (uns0 << 12) | ((uint32_t)n << 16);
-        const float f = (float)rw(s, a);
+        const float f = (float)rw(s, a, (p >> 4) & 1);
         std::memcpy(&lut[GC_PAIR_LUT_PAIRS + p].y, &f, sizeof(f));
     }
     *unsafe_rows = 0;

@@ -24,10 +24,11 @@ class PriorKnowledge:
     """What the agent is told about a polarisation-family env (cells3states3actions3.py:225-295)."""
 
     def __init__(self, n_cells=3, n_levels=3, default_reward=tables.right_polarizing,
-                 cell_classes=('moderators', 'children'), cell_labelling=None, **kwargs):
+                 cell_classes=('moderators', 'children'), cell_labelling=None, n_level_actions=None, **kwargs):
+        n_level_actions = n_levels if n_level_actions is None else n_level_actions
         self.state_space = [range(0, n_levels) for _ in range(n_cells)]
         self.n_cells = n_cells
-        self.action_space = [range(0, n_levels)] * n_cells
+        self.action_space = [range(0, n_level_actions)] * n_cells
         self.reward_range = (0, 1)
         self.initial_state = tuple([0] * n_cells)
         self.cell_classes = list(cell_classes)
@@ -39,8 +40,8 @@ class PriorKnowledge:
             self.reward_func = kwargs.get('reward_func', default_reward)
         self.n_states = n_levels ** n_cells
         self.n_intracellular_states = n_levels
-        self.n_intracellular_actions = n_levels
-        self.n_actions = n_levels ** n_cells
+        self.n_intracellular_actions = n_level_actions
+        self.n_actions = n_level_actions ** n_cells
 
     def cellularize(self, element, space):
         return list(element)
@@ -59,13 +60,17 @@ class PriorKnowledge:
 
 
 class _CellularEnv(gym.Env):
-    _n_cells, _n_levels = 3, 3
+    _n_cells, _n_levels, _n_level_actions = 3, 3, None
     _stochastic = False
     _default_reward = tables.right_polarizing
     _cell_classes = ('moderators', 'children')
+    _cell_labelling = None
+    _tables = None                    # explicit table set (debug MDPs), else the polarisation rules
+    _se_fill = 'silent'               # what rows >= 1 of the side-effects matrix hold
 
     def __init__(self, **kwargs):
         C, S = self._n_cells, self._n_levels
+        A = S if self._n_level_actions is None else self._n_level_actions
         self._kwargs = dict(kwargs)
         if self._stochastic:                       # cells3resetVdeadlock.py:77-83
             self.env_seed = kwargs.get('env_seed')
@@ -73,13 +78,14 @@ class _CellularEnv(gym.Env):
                 self.env_seed = int(str(time.time_ns())[-9:])
             self.deadlock = kwargs.get('deadlock', False)
         self.prior_knowledge = PriorKnowledge(n_cells=C, n_levels=S, default_reward=self._default_reward,
-                                              cell_classes=self._cell_classes, **kwargs)
+                                              cell_classes=self._cell_classes, n_level_actions=A,
+                                              cell_labelling=self._cell_labelling, **kwargs)
         self.n_cells = C
         self.initial_state = self.prior_knowledge.initial_state
         self.reward_func = kwargs.get('reward_func', self._default_reward)
         self.state_space = gym.spaces.Tuple([gym.spaces.Discrete(n=S, start=0) for _ in range(C)])
         self.observation_space = self.state_space
-        self.action_space = gym.spaces.Tuple([gym.spaces.Discrete(n=S, start=0)] * C)
+        self.action_space = gym.spaces.Tuple([gym.spaces.Discrete(n=A, start=0)] * C)
         self.difficulty = kwargs.get('difficulty', 'easy')
         self.data = {}
         self._vec = None
@@ -89,8 +95,13 @@ class _CellularEnv(gym.Env):
         if self._vec is None:
             from .vector_env import CellularVectorEnv
             extra = dict(stochastic=True, deadlock=self.deadlock, env_seed=self.env_seed) if self._stochastic else {}
-            self._vec = CellularVectorEnv(kind="cellular", num_envs=1, n_cells=self._n_cells, n_states=self._n_levels,
-                                          difficulty=self.difficulty, reward_func=self.reward_func, **extra)
+            if self._tables is not None:
+                self._vec = CellularVectorEnv(kind="cellular", num_envs=1, cell_tables=self._tables(),
+                                              env_seed=kwargs_seed(self._kwargs), rng_episodic=False)
+            else:
+                self._vec = CellularVectorEnv(kind="cellular", num_envs=1, n_cells=self._n_cells,
+                                              n_states=self._n_levels, difficulty=self.difficulty,
+                                              reward_func=self.reward_func, **extra)
         return self._vec
 
     @property
@@ -104,7 +115,7 @@ class _CellularEnv(gym.Env):
             self._vec.set_state(np.array(self._state, np.int8).reshape(self.n_cells, 1))
 
     def _side_effects_matrix(self, row0):
-        m = np.full((self.n_cells, self.n_cells), 'silent', dtype='<U6')
+        m = np.full((self.n_cells, self.n_cells), self._se_fill, dtype='<U6')
         m[0, :] = tables.SE_NAMES[np.asarray(row0)]
         return m
 
@@ -166,6 +177,54 @@ class Cells3ResetVDeadlockEnv(_CellularEnv):
     """gym_cellular/envs/cells3resetVdeadlock.py:70 (default reward: log2(1 + right_polarizing), :29-31, 88-91)"""
     _stochastic = True
     _default_reward = tables.nonlinear_right_polarizing
+
+
+def kwargs_seed(kwargs):
+    return int(kwargs.get('env_seed', 0) or 0)
+
+
+def _debug_reward(state, action, next_state):
+    """debug/debug.py:183-188"""
+    return sum(0.4 for s, a in zip(state, action) if s == 1 and a == 0) + 0.0
+
+
+def _deep_planning_reward(state, action, next_state):
+    """debug/deep_planning.py:11-18"""
+    return sum(0.05 if a == 0 else (0.5 if s == 3 else 0.0) for s, a in zip(state, action)) + 0.0
+
+
+def _deep_exploration_reward(state, action, next_state):
+    """debug/deep_exploration.py:11-16"""
+    return sum(0.5 for n in next_state if n == 1) + 0.0
+
+
+class DebugEnv(_CellularEnv):
+    """gym_cellular/envs/debug/debug.py:7"""
+    _n_cells, _n_levels, _n_level_actions = 2, 2, 2
+    _default_reward = staticmethod(_debug_reward)
+    _cell_classes = ()
+    _cell_labelling = [[], []]
+    _tables = staticmethod(tables.debug_tables)
+
+
+class DeepPlanningDebugEnv(_CellularEnv):
+    """gym_cellular/envs/debug/deep_planning.py:25"""
+    _n_cells, _n_levels, _n_level_actions = 2, 4, 2
+    _default_reward = staticmethod(_deep_planning_reward)
+    _cell_classes = ('regulators',)
+    _cell_labelling = [[0], [0]]
+    _tables = staticmethod(tables.deep_planning_tables)
+    _se_fill = 'safe'
+
+
+class DeepExplorationDebugEnv(_CellularEnv):
+    """gym_cellular/envs/debug/deep_exploration.py:23 (draws come from Philox keyed by `env_seed`)"""
+    _n_cells, _n_levels, _n_level_actions = 2, 4, 2
+    _default_reward = staticmethod(_deep_exploration_reward)
+    _cell_classes = ('regulators',)
+    _cell_labelling = [[0], [0]]
+    _tables = staticmethod(tables.deep_exploration_tables)
+    _se_fill = 'safe'
 
 
 # ---------------------------------------------------------------------------------------------

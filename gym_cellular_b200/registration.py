@@ -8,6 +8,9 @@ ENV_IDS = {
     "gym_cellular/Cells2Rest3-v0": ("gym_cellular_b200.envs:Cells2Rest3Env", "Cells2Rest3Vec"),
     "gym_cellular/Cells3ResetVDeadlock-v0": ("gym_cellular_b200.envs:Cells3ResetVDeadlockEnv", "Cells3ResetVDeadlockVec"),
     "gym_cellular/GridWorld-v0": ("gym_cellular_b200.envs:GridWorldEnv", "GridWorldVec"),
+    "gym_cellular/Debug-v0": ("gym_cellular_b200.envs:DebugEnv", "DebugVec"),
+    "gym_cellular/DeepPlanningDebug-v0": ("gym_cellular_b200.envs:DeepPlanningDebugEnv", "DeepPlanningDebugVec"),
+    "gym_cellular/DeepExplorationDebug-v0": ("gym_cellular_b200.envs:DeepExplorationDebugEnv", "DeepExplorationDebugVec"),
 }
 
 
@@ -26,6 +29,22 @@ def Cells3ResetVDeadlockVec(num_envs=1, **kwargs):
 
 def GridWorldVec(num_envs=1, **kwargs):
     return CellularVectorEnv(kind="gridworld", num_envs=num_envs, **kwargs)
+
+
+def DebugVec(num_envs=1, **kwargs):
+    from . import tables
+    return CellularVectorEnv(kind="cellular", num_envs=num_envs, cell_tables=tables.debug_tables(), **kwargs)
+
+
+def DeepPlanningDebugVec(num_envs=1, **kwargs):
+    from . import tables
+    return CellularVectorEnv(kind="cellular", num_envs=num_envs, cell_tables=tables.deep_planning_tables(), **kwargs)
+
+
+def DeepExplorationDebugVec(num_envs=1, **kwargs):
+    from . import tables
+    kwargs.setdefault("rng_episodic", False)
+    return CellularVectorEnv(kind="cellular", num_envs=num_envs, cell_tables=tables.deep_exploration_tables(), **kwargs)
 
 
 def register_all():

@@ -196,3 +196,49 @@ def counted_levels(n_states):
     out = np.zeros(n_states, np.uint8)
     out[n_states - 1] = 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# The three debug MDPs (gym_cellular/envs/debug/*.py) as table sets of the same cellular kernel.
+# Each returns the dict `CellularVectorEnv(cell_tables=...)` takes.
+
+def debug_tables():
+    """Debug-v0 (debug/debug.py:76-116, 183-188): 2 cells x 2 levels x 2 actions, next = level XOR
+    action, reward 0.4 per cell at level 1 choosing action 0, incidence = cells at level 1 / 2,
+    (0,1) reports entry 1 'unsafe' and entry 0 'safe', (0,0) reports entry 0 'safe'."""
+    move = np.array([[0, 1], [1, 0]], np.int8)
+    reward = np.array([[0.0, 0.0], [0.4, 0.0]])
+    se = np.zeros((2, 2, 2), np.int8)           # [entry j][s'_0][s'_1]
+    se[0, 0, 0] = SAFE
+    se[0, 0, 1] = SAFE
+    se[1, 0, 1] = UNSAFE
+    return dict(n_cells=2, n_states=2, n_actions=2, move=move, reward=reward, side_effects=se,
+                counted=np.array([0, 1], np.uint8), reset_row=[SAFE, SILENT], se_fill=SILENT)
+
+
+def deep_planning_tables():
+    """DeepPlanningDebug-v0 (debug/deep_planning.py:11-18, 81-100): 2 cells x 4 levels x 2 actions;
+    action 0 stays (reward 0.05), action 1 advances modulo 4 (reward 0.5 from level 3); every
+    side-effect entry is 'safe' and the incidence is 0."""
+    move = np.array([[s, (s + 1) % 4] for s in range(4)], np.int8)
+    reward = np.array([[0.05, 0.5 if s == 3 else 0.0] for s in range(4)])
+    return dict(n_cells=2, n_states=4, n_actions=2, move=move, reward=reward,
+                side_effects=np.full((2, 4, 4), SAFE, np.int8), counted=np.zeros(4, np.uint8),
+                reset_row=[SAFE, SAFE], se_fill=SAFE)
+
+
+def deep_exploration_tables():
+    """DeepExplorationDebug-v0 (debug/deep_exploration.py:11-16, 79-119): 2 cells x 4 levels x 2 actions;
+    action 1 steps down (not below 0); action 0 draws u: below 1/2 it steps down (stays at 0), else
+    it steps up -- except that levels 0 and 1 are capped at 1 (the reference compares against
+    n_cells - 1).  Reward 1/2 per cell whose NEXT level is 1.  Levels 2 and 3 are only
+    reachable by assigning env.state; from level 3 the reference would walk up to level 4, outside its
+    own Discrete(4): the table keeps the cell at 3 there (documented deviation, unreachable from reset)."""
+    S = 4
+    hi = np.array([[min(s + 1, 1) if s <= 1 else min(s + 1, S - 1), max(s - 1, 0)] for s in range(S)], np.int8)
+    lo = np.array([[max(s - 1, 0), max(s - 1, 0)] for s in range(S)], np.int8)
+    draws = np.array([[1, 0]] * S, np.uint8)
+    rew = lambda nxt: (np.asarray(nxt) == 1) * 0.5
+    return dict(n_cells=2, n_states=S, n_actions=2, move=hi, noisy=lo, draws=draws, reward=rew(hi),
+                reward_noisy=rew(lo), side_effects=np.full((2, S, S), SAFE, np.int8),
+                counted=np.zeros(S, np.uint8), reset_row=[SAFE, SAFE], se_fill=SAFE, noise_prob=0.5)

@@ -69,7 +69,7 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                  difficulty="easy", reward_func=None, stochastic=False, deadlock=False,
                  noise_prob=0.1, dispersal_prob=0.01, env_seed=0, rng_episodic=None,
                  max_episode_steps=None, device=None, env_id_offset=0, emit_side_effects=True,
-                 collect_stats=True, host_chunk_envs=1 << 20):
+                 collect_stats=True, host_chunk_envs=1 << 20, cell_tables=None):
         self._lib = _lib.load()                      # raises ImportError when the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("CellularVectorEnv needs a CUDA device: there is no CPU fallback")
@@ -79,6 +79,12 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.kind = kind
+        self._cell_tables = cell_tables
+        if cell_tables is not None:          # explicit table set (tables.debug_tables() etc.)
+            n_cells, n_states, n_actions = (cell_tables[k] for k in ("n_cells", "n_states", "n_actions"))
+            stochastic = cell_tables.get("draws") is not None
+            noise_prob = cell_tables.get("noise_prob", noise_prob)
+            reward_func = cell_tables["reward"] if reward_func is None else reward_func
         if kind == "gridworld":
             n_cells, n_states, n_actions, stochastic = 2, 20, 5, True
         elif kind != "cellular":
@@ -162,18 +168,25 @@ class CellularVectorEnv(gym.vector.VectorEnv):
     # ------------------------------------------------------------------------------------------
     def _set_tables(self):
         S, A, Cn = self.n_states, self.n_actions, self.n_cells
-        if self.stochastic:
+        ct = self._cell_tables
+        reward_noisy, counted = None, tables.counted_levels(S)
+        if ct is not None:
+            move, noisy, draws, se = ct["move"], ct.get("noisy"), ct.get("draws"), ct["side_effects"]
+            reward_noisy, counted = ct.get("reward_noisy"), ct["counted"]
+        elif self.stochastic:
             move, noisy, draws = tables.noise_tables(S, A, self.deadlock)
+            se = tables.side_effect_tables(Cn, S, self.difficulty)
         else:
             move, noisy, draws = tables.move_table(S, A), None, None
-        se = tables.side_effect_tables(Cn, S, self.difficulty)
+            se = tables.side_effect_tables(Cn, S, self.difficulty)
         keep = [np.ascontiguousarray(move, np.int8),
                 None if noisy is None else np.ascontiguousarray(noisy, np.int8),
                 None if draws is None else np.ascontiguousarray(draws, np.uint8),
                 np.ascontiguousarray(self.reward_table, np.float32),
                 np.ascontiguousarray(se, np.int8),
-                np.ascontiguousarray(tables.counted_levels(S), np.uint8),
-                np.zeros(Cn, np.int8)]
+                np.ascontiguousarray(counted, np.uint8),
+                np.zeros(Cn, np.int8),
+                None if reward_noisy is None else np.ascontiguousarray(reward_noisy, np.float32)]
         t = _lib.GcCellTables(*[None if a is None else a.ctypes.data for a in keep])
         _lib.check(self._lib.gc_set_tables(self._h, C.byref(t)))
         self.side_effect_table = se
@@ -199,6 +212,45 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if dtype == torch.int32:
             return idx
         return idx.to(torch.int64) & 0xFFFFFFFF
+
+    # ---- batched codec: both directions, states and actions -----------------------
+    def tabularize(self, cells, space="state"):
+        """int8 [n_cells, n] device tensor (n a multiple of 16, contiguous) -> int64 [n] tabular indices.
+        `space`: 'state' or 'action' (radix n_states or n_actions; grid world 20 / 5), i.e. the batched
+        `prior_knowledge.tabularize` (cells3states3actions3.py:281-284, grid_world.py:397-407)."""
+        cells = torch.as_tensor(cells, device=self.device).to(torch.int8).contiguous()
+        n = cells.shape[1]
+        ld = _round_up(n, 16)
+        if ld != n:
+            pad = torch.zeros(cells.shape[0], ld, dtype=torch.int8, device=self.device)
+            pad[:, :n] = cells
+            cells = pad
+        radix = self.n_states if space == "state" else self.n_actions
+        out = torch.empty(ld, dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.gc_encode(self.device.index, n, ld, cells.shape[0], radix, _ptr(cells), _ptr(out), self._stream()))
+        return out[:n].to(torch.int64) & 0xFFFFFFFF
+
+    def detabularize(self, index, space="state"):
+        """int64/int32 [n] tabular indices -> int8 [n_cells, n] cells: the batched
+        `prior_knowledge.detabularize` (generalized_space_transformations.py:15-23)."""
+        index = torch.as_tensor(index, device=self.device)
+        n = index.shape[0]
+        ld = _round_up(n, 16)
+        idx = torch.zeros(ld, dtype=torch.int32, device=self.device)
+        idx[:n] = (index.to(torch.int64) & 0xFFFFFFFF).to(torch.int32) if index.dtype != torch.int32 else index
+        radix = self.n_states if space == "state" else self.n_actions
+        out = torch.empty(self.n_cells, ld, dtype=torch.int8, device=self.device)
+        _lib.check(self._lib.gc_decode(self.device.index, n, ld, self.n_cells, radix, _ptr(idx), _ptr(out), self._stream()))
+        return out[:, :n]
+
+    def materialise(self, i):
+        """Observation of env i in the reference's own Python type: a tuple of ints (polarisation
+        family) or a tuple of {'agt': ..., 'living_trees': ...} dicts (grid world, grid_world.py:364-394)."""
+        codes = [int(x) for x in self._state[:, i].cpu().tolist()]
+        if self.kind == "gridworld":
+            from .envs import GridWorldPriorKnowledge
+            return GridWorldPriorKnowledge().decellularize(codes, "state")
+        return tuple(codes)
 
     @property
     def time_step(self):
@@ -232,7 +284,10 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             # the reference's reset() info: cellular envs hard-code row 0 = ('safe', 'silent', ...)
             # (cells3states3actions3.py:102-109); grid world evaluates side_effects_func (grid_world.py:101)
             self._se_row.zero_()
-            if self.kind == "cellular":
+            if self._cell_tables is not None:
+                for c, code in enumerate(self._cell_tables["reset_row"]):
+                    self._se_row[c].fill_(int(code))
+            elif self.kind == "cellular":
                 self._se_row[0].fill_(tables.SAFE)
             else:
                 self._se_row.fill_(tables.SAFE)

@@ -103,6 +103,8 @@ typedef struct {
  *   noisy  [S][A] int8   next level when the draw fires    (cells3resetVdeadlock.py:37-41)
  *   draws  [S][A] uint8  1 if (level, action) consumes a draw (cells3resetVdeadlock.py:49-60)
  *   reward [S][A] float  per-cell reward of the OLD level  (cells3states3actions3.py:9-45)
+ *   reward_noisy [S][A] float  optional: per-cell reward when the draw fired, for rewards that depend on
+ *          the NEXT level (debug/deep_exploration.py:11-16); NULL = same as `reward`
  *   side_effects [C][S][S] int8  code (0 silent, 1 safe, 2 unsafe) of row-0 entry j of the
  *          side-effects matrix as a function of (s'_0, s'_p), p = 1 for j = 0 and p = j otherwise
  *          (cells3states3actions3.py:157-212; only row 0 is ever written by the reference)
@@ -117,6 +119,7 @@ typedef struct {
     const int8_t  *side_effects;
     const uint8_t *counted;
     const int8_t  *initial_state;
+    const float   *reward_noisy;
 } gc_cell_tables;
 
 int         gc_abi_version(void);

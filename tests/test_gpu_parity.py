@@ -428,3 +428,69 @@ def test_config3_full_size_properties(B):
         assert bool((env.tabular_state() == st[0].to(torch.int64) + 20 * st[1].to(torch.int64)).all())
     env.check_actions()
     assert env.stats()["episodes_truncated"] == 2 * n
+
+
+# ---------------------------------------------------------------------------------------------
+# batched codec both ways, reference-typed materialisation, exact model export
+
+def test_batched_codec_and_materialise(B, O, golden_gw):
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=128)
+    st = golden_gw["gw_states"]
+    env.set_state(st.T.copy())
+    tab = env.tabularize(env.state)
+    assert (host(tab) == st[:, 0].astype(int) + 20 * st[:, 1].astype(int)).all()
+    assert (host(env.detabularize(tab)) == st.T).all()
+    acts = golden_gw["gw_actions"]                                    # 24 actions: ragged (not a multiple of 16)
+    assert (host(env.tabularize(dev(acts.T), "action")) == golden_gw["gw_action_tab"]).all()
+    assert (host(env.detabularize(dev(golden_gw["gw_action_tab"]), "action")) == acts.T).all()
+    obj = env.materialise(5)
+    dec = golden_gw["gw_states_decoded"][5]
+    J = int(dec[0])
+    assert (obj[J]["agt"]["position"] == dec[1:3]).all() and (obj[0]["living_trees"].reshape(-1) == dec[3:7]).all()
+    pol = B.CellularVectorEnv(num_envs=20, n_cells=16, n_states=4)
+    cells = np.random.default_rng(0).integers(0, 4, (16, 20)).astype(np.int8)
+    pol.set_state(cells)
+    assert (host(pol.tabularize(pol.state)).astype(np.uint32) == O.encode(cells, 4)).all()
+    assert pol.materialise(3) == tuple(int(x) for x in cells[:, 3])
+
+
+def test_exact_model_export(B, golden_pol, golden_gw):
+    from gym_cellular_b200.model import exact_model
+    # deterministic 3-cell env: a permutation-like 0/1 model that reproduces the reference's table
+    P, R, valid = exact_model("cellular")
+    assert P.shape == (27, 27, 27) and valid.all() and ((P == 0) | (P == 1)).all() and (P.sum(2) == 1).all()
+    assert (P.reshape(729, 27).argmax(1) == golden_pol["c3_next_tab"]).all()
+    np.testing.assert_allclose(R.reshape(-1), golden_pol["c3_reward_right_polarizing"], rtol=1e-6)
+    # stochastic env: probabilities of the reference's enumerated noise patterns
+    P, R, _ = exact_model("cellular", stochastic=True)
+    np.testing.assert_allclose(P.sum(2), 1.0, atol=1e-12)
+    sa, u, nxt = golden_pol["noise_rs_sa"], golden_pol["noise_rs_u"], golden_pol["noise_rs_next"]
+    want = np.zeros_like(P)
+    for (si, ai), uu, ns in zip(sa, u, nxt):
+        w = np.prod([1.0 if np.isnan(x) else (0.1 if x < 0.1 else 0.9) for x in uu])
+        want[si, ai, ns[0] + 3 * ns[1] + 9 * ns[2]] += w
+    np.testing.assert_allclose(P, want, atol=1e-12)
+    # grid world: 9 outcomes per (state, action); compare with the reference's enumeration
+    P, R, valid = exact_model("gridworld")
+    assert valid.sum() == 128
+    np.testing.assert_allclose(P[valid].sum(2), 1.0, atol=1e-12)
+    g = golden_gw
+    s_tab = g["gw_case_state"][:, 0].astype(int) + 20 * g["gw_case_state"][:, 1].astype(int)
+    a_tab = g["gw_case_action"][:, 0].astype(int) + 5 * g["gw_case_action"][:, 1].astype(int)
+    w = np.where(g["gw_case_u0"] < 0.01, 0.01 / 32, 0.99)            # 16 bit patterns x 2 jurisdictions
+    want = np.zeros_like(P)
+    np.add.at(want, (s_tab, a_tab, g["gw_case_tab"]), w)
+    Rw = np.zeros_like(R)
+    np.add.at(Rw, (s_tab, a_tab), w * g["gw_case_reward"])
+    covered = np.zeros(P.shape[:2], bool)
+    covered[s_tab, a_tab] = True
+    np.testing.assert_allclose(P[covered], want[covered], atol=1e-9)
+    np.testing.assert_allclose(R[covered], Rw[covered], atol=1e-6)
+
+
+def test_make_vec_entry_point(B):
+    from gym_cellular_b200._gym import gym
+    env = gym.make_vec("gym_cellular/GridWorld-v0", num_envs=64, max_episode_steps=128)
+    obs, info = env.reset()
+    assert env.num_envs == 64 and len(obs) == 2 and (host(info["tabular_state"]) == 375).all()
+    env.close()
