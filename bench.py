@@ -360,6 +360,22 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
         g_ms, g_steps = time_graph_path(batches, steps, device)
         graph_res = {"value": n_rank * g_steps / (g_ms * 1e-3), "ms_per_step": g_ms / g_steps,
                      "steps_per_graph": RING}
+    ro_res = None
+    if dist is None:                       # K-step fused rollout (random actions generated in the kernel)
+        K = 64
+        for b in batches:
+            b["env"].rollout(K)
+        torch.cuda.synchronize(device)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 4
+        r0.record()
+        for _ in range(reps):
+            for b in batches:
+                b["env"].rollout(K)
+        r1.record()
+        r1.synchronize()
+        ro_res = {"value": n_rank * K * reps / (r0.elapsed_time(r1) * 1e-3), "steps_per_launch": K,
+                  "note": "fused rollout: state in registers, actions generated in-kernel (not per-step step())"}
     el_host, h2d, d2h = time_host_path(batches, e2e_steps, 2, dist, device)
     # the only collective of the path: episode statistics, all-reduced once per iteration (NCCL, side stream)
     from gym_cellular_b200.distributed import StatsReducer
@@ -382,6 +398,7 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
                      "l2_resident": WORKLOADS[workload]["l2_resident"]},
         "episode_stats": totals,
         "cuda_graph": graph_res,
+        "fused_rollout": ro_res,
     }
     for b in batches:
         b["env"].close()
@@ -432,7 +449,7 @@ def main():
                 extra[w] = {"description": WORKLOADS[w]["desc"], "value": r["value"], "ms_per_step": r["ms_per_step"],
                             "roofline_frac": r["roofline"]["frac"], "achieved_gbs": r["roofline"]["achieved"],
                             "l2_resident": WORKLOADS[w]["l2_resident"], "e2e": r["e2e"]["value"],
-                            "kernels_per_step": r["roofline"]["kernels_per_step"], "cuda_graph": r["cuda_graph"]}
+                            "kernels_per_step": r["roofline"]["kernels_per_step"], "cuda_graph": r["cuda_graph"], "fused_rollout": r["fused_rollout"]}
     if rank == 0:
         line = {
             "metric": "env-steps/sec", "value": main_res["value"], "unit": "env-steps/s", "n_gpus": world,
@@ -448,6 +465,7 @@ def main():
             "e2e": {**main_res["e2e"], "pcie_measured": measure_pcie(device)},
             "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
             "roofline": main_res["roofline"], "episode_stats": main_res["episode_stats"],
+            "fused_rollout": main_res["fused_rollout"],
         }
         if extra:
             line["workloads"] = extra

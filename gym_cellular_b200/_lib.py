@@ -15,10 +15,11 @@ F_NOISE, F_RNG_EPISODIC, F_REWARD_LOG2 = 1, 4, 16
 MAX_CELLS, MAX_LEVELS, N_STATS = 16, 8, 8
 STAT_STEPS, STAT_UNSAFE, STAT_COUNT, STAT_TRUNCATED, STAT_REWARD_Q24 = range(5)
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_ACTION = 0, -1, -2, -3, -4
+POLICY_RANDOM, POLICY_TABLE = 0, 1
 
 EXPORTS = ["gc_abi_version", "gc_last_error", "gc_create", "gc_destroy", "gc_set_tables",
            "gc_set_global_step", "gc_get_global_step", "gc_sync_global_step", "gc_launch_count", "gc_reset", "gc_step",
-           "gc_step_host", "gc_poll_status", "gc_encode", "gc_decode"]
+           "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode", "gc_decode"]
 
 
 class GcConfig(C.Structure):
@@ -70,6 +71,7 @@ def load():
     L.gc_reset.argtypes = [vp] * 6
     L.gc_step.argtypes = [vp, i64, i64] + [vp] * 13
     L.gc_step_host.argtypes = [vp] * 21 + [i64]
+    L.gc_rollout.argtypes = [vp, C.c_int32, C.c_int32] + [vp] * 8
     L.gc_poll_status.argtypes = [vp, vp]
     L.gc_encode.argtypes = [C.c_int, i64, i64, C.c_int32, C.c_int32, vp, vp, vp]
     L.gc_decode.argtypes = [C.c_int, i64, i64, C.c_int32, C.c_int32, vp, vp, vp]

@@ -408,6 +408,44 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
     return GC_OK;
 }
 
+int gc_rollout(gc_env *env, int32_t n_steps, int32_t policy_kind, const int32_t *policy, int8_t *state,
+               int32_t *t, uint32_t *index, float *ret, int32_t *n_unsafe, int64_t *stats, void *stream)
+{
+    if (int rc = check_env(env)) return rc;
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    if (!state || !t || !index || !ret || !n_unsafe) return fail(GC_ERR_INVALID, "a required device pointer is NULL");
+    if (n_steps < 1) return fail(GC_ERR_INVALID, "n_steps must be >= 1");
+    if (policy_kind != GC_POLICY_RANDOM && policy_kind != GC_POLICY_TABLE) return fail(GC_ERR_INVALID, "unknown policy kind");
+    if (policy_kind == GC_POLICY_TABLE && !policy) return fail(GC_ERR_INVALID, "GC_POLICY_TABLE needs a policy table");
+    if (env->cfg.kind == GC_KIND_CELLULAR && !env->fast_ok)
+        return fail(GC_ERR_INVALID, "gc_rollout supports the cellular family with n_states, n_actions <= 4 only");
+    GC_CUDA(cudaSetDevice(env->cfg.device));
+    RolloutIO io;
+    io.state = state; io.t = t; io.index = index; io.ret = ret; io.n_unsafe = n_unsafe; io.policy = policy;
+    io.stats = reinterpret_cast<unsigned long long *>(stats);
+    io.status = env->d_status;
+    io.n = env->cfg.n_envs; io.ld = env->cfg.ld; io.env_id_offset = env->cfg.env_id_offset;
+    const uint32_t lo = static_cast<uint32_t>(env->cfg.seed), hi = static_cast<uint32_t>(env->cfg.seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        io.round_key[2 * r] = lo + static_cast<uint32_t>(r) * 0x9E3779B9u;
+        io.round_key[2 * r + 1] = hi + static_cast<uint32_t>(r) * 0xBB67AE85u;
+    }
+    io.step_ctr = env->d_step; io.done_ctr = env->d_done;
+    io.episodic = (env->cfg.flags & GC_F_RNG_EPISODIC) ? 1 : 0;
+    io.max_episode_steps = env->cfg.max_episode_steps;
+    io.n_steps = n_steps; io.policy_kind = policy_kind;
+    cudaError_t e;
+    if (env->cfg.kind == GC_KIND_CELLULAR)
+        e = gc_launch_cell_rollout(env->tab, io, env->d_pair_lut, (env->cfg.flags & GC_F_NOISE) != 0, env->n_sm,
+                                   static_cast<cudaStream_t>(stream));
+    else
+        e = gc_launch_grid_rollout(env->grid, io, env->n_sm, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "rollout kernel launch failed: %s", cudaGetErrorString(e));
+    env->launches += 1;
+    env->global_step += n_steps;
+    return GC_OK;
+}
+
 int gc_poll_status(gc_env *env, void *stream)
 {
     if (int rc = check_env(env)) return rc;

@@ -21,7 +21,6 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 
 // resident blocks per SM the register budget is sized for: all 2C row words of a thread's 4 envs are
 // requested up front (memory-level parallelism), so wide envs trade occupancy for loads in flight

@@ -26,6 +26,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int e) { return (w >> (8 * e)) & 0xFFu; }
 
 // streaming accesses: every byte is used once, keep it out of L1
@@ -61,18 +63,20 @@ __device__ __forceinline__ uint32_t launch_step_counter(const StepIO &io)
 // Called by every thread at kernel exit: the last block to arrive advances the device step counter.
 // Every thread read the counter at kernel entry, before its block's arrival, so no block can observe
 // the incremented value within the same launch.
-__device__ __forceinline__ void tick_step_counter(const StepIO &io)
+__device__ __forceinline__ void tick_step_counter(const uint32_t *step_ctr, uint32_t *done_ctr, uint32_t inc)
 {
-    if (io.step_ctr == nullptr) return;
+    if (step_ctr == nullptr) return;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t arrived = atomicAdd(io.done_ctr, 1u);
+        const uint32_t arrived = atomicAdd(done_ctr, 1u);
         if (arrived == gridDim.x - 1) {
-            *io.done_ctr = 0u;
-            *const_cast<uint32_t *>(io.step_ctr) = *reinterpret_cast<const volatile uint32_t *>(io.step_ctr) + 1u;
+            *done_ctr = 0u;
+            *const_cast<uint32_t *>(step_ctr) = *reinterpret_cast<const volatile uint32_t *>(step_ctr) + inc;
         }
     }
 }
+
+__device__ __forceinline__ void tick_step_counter(const StepIO &io) { tick_step_counter(io.step_ctr, io.done_ctr, 1u); }
 
 // byte mask of the envs of a 4-env word that lie inside the launch range (rem = envs left, >= 1)
 __device__ __forceinline__ uint32_t valid_bytes(int rem) { return rem >= 4 ? 0xFFFFFFFFu : ((1u << (8 * rem)) - 1u); }

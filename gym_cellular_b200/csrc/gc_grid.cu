@@ -10,7 +10,6 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 
 template <int RNG>
 __global__ void __launch_bounds__(kThreads, 4)

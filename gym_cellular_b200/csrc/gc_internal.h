@@ -35,6 +35,24 @@ struct StepIO {
     int32_t  max_episode_steps;
 };
 
+// K-step fused rollout (gc_rollout.cu): state stays in registers for n_steps steps, actions are
+// generated in the kernel (uniformly random, or from a tabular policy).
+struct RolloutIO {
+    int8_t       *state;
+    int32_t      *t;
+    uint32_t     *index;
+    float        *ret;          // [ld] out: sum of the rewards of the n_steps steps
+    int32_t      *n_unsafe;     // [ld] out: steps that reported 'unsafe'
+    const int32_t *policy;      // GC_POLICY_TABLE: tabular action index per tabular state, else NULL
+    unsigned long long *stats;
+    unsigned long long *status;
+    int64_t n, ld, env_id_offset;
+    uint32_t round_key[20];
+    const uint32_t *step_ctr;
+    uint32_t *done_ctr;
+    int32_t episodic, max_episode_steps, n_steps, policy_kind;
+};
+
 // Constant tables of the cellular family, passed by value as a __grid_constant__ parameter and
 // staged into shared memory once per block.
 struct CellTables {
@@ -85,6 +103,9 @@ cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng
 #define GC_PAIR_LUT_ENTRIES (GC_PAIR_LUT_PAIRS + 32)
 cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode,
                                      int n_sm, cudaStream_t stream);
+cudaError_t gc_launch_cell_rollout(const CellTables &tab, const RolloutIO &io, const uint2 *lut, bool noise,
+                                   int n_sm, cudaStream_t stream);
+cudaError_t gc_launch_grid_rollout(const GridParams &gp, const RolloutIO &io, int n_sm, cudaStream_t stream);
 cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm,
                                 cudaStream_t stream);
 cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,

@@ -345,6 +345,28 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                 check(rc)
         return launch
 
+    def rollout(self, n_steps, policy=None):
+        """Fused K-step rollout: `n_steps` steps per env inside one kernel, actions generated on the
+        device -- uniformly at random (policy=None) or from a tabular policy (int tensor
+        [n_states ** n_cells] of tabular action indices).  Returns (returns float32 [num_envs],
+        unsafe_steps int32 [num_envs]); state, time_step, tabular_state() and stats() advance exactly as
+        if step() had been called n_steps times with those actions."""
+        n = self.num_envs
+        if getattr(self, "_ro_ret", None) is None:
+            self._ro_ret = torch.zeros(self.ld, dtype=torch.float32, device=self.device)
+            self._ro_unsafe = torch.zeros(self.ld, dtype=torch.int32, device=self.device)
+        kind, ptab = _lib.POLICY_RANDOM, None
+        if policy is not None:
+            ptab = torch.as_tensor(policy, device=self.device).to(torch.int32).contiguous()
+            if ptab.numel() != self.n_states ** self.n_cells:
+                raise ValueError("policy must have one entry per tabular state")
+            kind = _lib.POLICY_TABLE
+        _lib.check(self._lib.gc_rollout(self._h, int(n_steps), kind, _ptr(ptab), _ptr(self._state), _ptr(self._t),
+                                        _ptr(self._index), _ptr(self._ro_ret), _ptr(self._ro_unsafe), _ptr(self._stats),
+                                        self._stream()))
+        self._graph_dirty = True
+        return self._ro_ret[:n], self._ro_unsafe[:n]
+
     def capture_steps(self, action_ring):
         """Captures one step per tensor of `action_ring` (int8 [n_cells, ld] device tensors, kept alive
         by the caller) into a CUDA graph and returns it; `graph.replay()` then runs len(action_ring)
@@ -471,8 +493,8 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
             _ptr(self._se_row), _ptr(self._stats), self.host_chunk_envs))
         obs = tuple(h["state"][c, :n] for c in range(self.n_cells))
+        # zero-copy views of the pinned mirrors (valid until the next step); incidence = count / n_cells
         infos = {"unsafe": h["unsafe"][:n].view(np.bool_), "count": h["count"][:n],
-                 "side_effects_incidence": h["count"][:n].astype(np.float32) / self.n_cells,
                  "tabular_state": h["index"][:n].view(np.uint32)}
         if "se_row" in h:
             infos["side_effects"] = h["se_row"][:, :n]

@@ -180,6 +180,22 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
                  uint8_t *d_unsafe, uint8_t *d_count, int8_t *d_se_row, int64_t *d_stats,
                  int64_t chunk_envs);
 
+/* K-step fused rollout (the caller's loop around step(): pick an action, step, accumulate).  Runs
+ * n_steps consecutive steps for every env of the shard inside ONE kernel; the state stays in
+ * registers, actions are generated in the kernel:
+ *   GC_POLICY_RANDOM  cellular: every cell draws uniformly from its actions; grid world: the
+ *                     distribution of the reference's action sampler (one jurisdiction named, uniform
+ *                     position; grid_world.py:191-195).  Philox, keyed like the step's noise.
+ *   GC_POLICY_TABLE   action = policy[tabular state] (device int32 [n_states^n_cells], tabular action
+ *                     index): `initial_policy` as a table (cells3states3actions3.py:293-295)
+ * The result is bit-identical to n_steps calls of gc_step with the same actions.  Cellular family:
+ * fast path only (n_states, n_actions <= 4).  ret [ld] float: sum of the n_steps rewards;
+ * n_unsafe [ld] int32: steps that reported 'unsafe'; state / t / index as in gc_step. */
+#define GC_POLICY_RANDOM 0
+#define GC_POLICY_TABLE  1
+int gc_rollout(gc_env *env, int32_t n_steps, int32_t policy_kind, const int32_t *policy, int8_t *state,
+               int32_t *t, uint32_t *index, float *ret, int32_t *n_unsafe, int64_t *stats, void *stream);
+
 /* Reads and clears the handle's device status word (synchronises `stream`).  Returns GC_OK or
  * GC_ERR_ACTION if some env received a grid-world action without any go-to position since the
  * last poll (the reference raises KeyError('position'), grid_world.py:143). */

@@ -541,6 +541,44 @@ int64_t gco_step(const gco_config *cfg, int64_t n, int64_t ld, const int8_t *act
     return 0;
 }
 
+/* Actions of the fused rollout (gym_cellular_b200/csrc/gc_rollout.cu), one step for every env:
+ *   policy_kind 0  random: the action word of env g for cell c at RNG counter T is word (g % 4) of
+ *                  philox(key, ctr = ((g/4)_lo, (g/4)_hi, T, 0x40000000 + c)); cellular: action =
+ *                  floor(word * 2^-32 * A); grid world (c = 0): jurisdiction = bit 31, position =
+ *                  bits 29-30, the other jurisdiction names no position (grid_world.py:191-195)
+ *   policy_kind 1  table: action = digits of policy[tabular state]
+ * T = episode step (GCO_F_RNG_EPISODIC) or the global step, as for the step's noise. */
+void gco_policy_actions(const gco_config *cfg, int64_t n, int64_t ld, int policy_kind, const int32_t *policy,
+                        const int8_t *state, const int32_t *t, int64_t global_step, int8_t *actions)
+{
+    const int C = cfg->n_cells;
+    uint32_t key[2] = {(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
+    for (int64_t e = 0; e < n; ++e) {
+        uint64_t g = (uint64_t)(cfg->env_id_offset + e);
+        uint32_t T = (cfg->flags & GCO_F_RNG_EPISODIC) ? (uint32_t)t[e] : (uint32_t)global_step;
+        if (policy_kind == 1) {
+            int cells[GCO_MAX_CELLS];
+            for (int c = 0; c < C; ++c) cells[c] = state[c * ld + e];
+            uint32_t p = (uint32_t)policy[uniform_radix_index(cells, C, cfg->kind == GCO_KIND_GRIDWORLD ? 20 : cfg->n_states)];
+            for (int c = 0; c < C; ++c) { actions[c * ld + e] = (int8_t)(p % (uint32_t)cfg->n_actions); p /= (uint32_t)cfg->n_actions; }
+            continue;
+        }
+        for (int c = 0; c < (cfg->kind == GCO_KIND_GRIDWORLD ? 1 : C); ++c) {
+            uint32_t ctr[4] = {(uint32_t)(g >> 2), (uint32_t)(g >> 34), T, 0x40000000u + (uint32_t)c};
+            uint32_t w[4];
+            philox4x32_10(ctr, key, w);
+            uint32_t word = w[g & 3];
+            if (cfg->kind == GCO_KIND_GRIDWORLD) {
+                int jur = (int)(word >> 31), pos = (int)((word >> 29) & 3u);
+                actions[0 * ld + e] = (int8_t)(jur == 0 ? pos : 4);
+                actions[1 * ld + e] = (int8_t)(jur == 1 ? pos : 4);
+            } else {
+                actions[c * ld + e] = (int8_t)(((uint64_t)word * (uint64_t)cfg->n_actions) >> 32);
+            }
+        }
+    }
+}
+
 /* Batched codec (generalized_space_transformations.py:1-23) on the SoA layout, uniform radix. */
 void gco_encode(int64_t n, int64_t ld, int n_cells, int radix, const int8_t *cells, uint32_t *index)
 {

@@ -55,6 +55,7 @@ def lib():
         L.gco_reset.argtypes = [C.POINTER(_Config), C.c_int64, C.c_int64, vp, vp, vp, vp]
         L.gco_initial_state.argtypes = [C.POINTER(_Config), vp]
         L.gco_n_slots.argtypes = [C.POINTER(_Config)]
+        L.gco_policy_actions.argtypes = [C.POINTER(_Config), C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int64, vp]
         L.gco_encode.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp]
         L.gco_decode.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp]
         L.gco_encode_one.restype = C.c_uint64
@@ -184,6 +185,24 @@ class OracleEnv:
         if lo == 0 and hi == self.n:
             self.global_step += 1
         return self.state, self.reward, self.terminated, self.truncated
+
+    def policy_actions(self, policy=None):
+        """Actions the fused rollout kernel generates for the current step (random or tabular policy)."""
+        a = np.zeros((self.C, self.n), np.int8)
+        pol = None if policy is None else np.ascontiguousarray(policy, np.int32)
+        lib().gco_policy_actions(C.byref(self.cfg), self.n, self.n, 0 if pol is None else 1, _p(pol),
+                                 _p(self.state), _p(self.t), self.global_step, _p(a))
+        return a
+
+    def rollout(self, n_steps, policy=None):
+        """n_steps x (policy_actions -> step); returns (sum of rewards, unsafe steps) per env."""
+        ret = np.zeros(self.n, np.float64)
+        uns = np.zeros(self.n, np.int64)
+        for _ in range(n_steps):
+            self.step(self.policy_actions(policy))
+            ret += self.reward
+            uns += self.unsafe
+        return ret, uns
 
     def step_parallel(self, actions, n_threads):
         """All-core stepping for the CPU baseline: ctypes releases the GIL inside gco_step."""

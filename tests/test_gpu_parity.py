@@ -494,3 +494,71 @@ def test_make_vec_entry_point(B):
     obs, info = env.reset()
     assert env.num_envs == 64 and len(obs) == 2 and (host(info["tabular_state"]) == 375).all()
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# K-step fused rollout == K x (generate actions, step), against the oracle
+
+def _check_rollout(env, ora, K, policy=None, reps=2):
+    n = env.num_envs
+    for _ in range(reps):
+        ret, uns = env.rollout(K, policy)
+        oret, ouns = ora.rollout(K, None if policy is None else host(policy) if hasattr(policy, "cpu") else policy)
+        assert (host(env.state) == ora.state).all()
+        assert (host(env.time_step) == ora.t).all()
+        assert (host(env.tabular_state()) == ora.index).all()
+        assert (host(uns) == ouns).all()
+        np.testing.assert_allclose(host(ret), oret, rtol=1e-5, atol=1e-6)
+    s = env.stats()
+    assert s["env_steps"] == ora.stats[0] == reps * K * n and s["unsafe_steps"] == ora.stats[1]
+    assert s["count_sum"] == ora.stats[2] and s["episodes_truncated"] == ora.stats[3]
+    assert abs(s["reward_sum"] * 2 ** 24 - ora.stats[4]) <= reps * K * n
+
+
+@pytest.mark.parametrize("n", [5, 10007])
+def test_rollout_deterministic_polarisation(B, O, n):
+    env = B.CellularVectorEnv(num_envs=n, env_seed=12, env_id_offset=4096, max_episode_steps=11)
+    ora = O.OracleEnv(n_envs=n, seed=12, env_id_offset=4096, max_episode_steps=11, rng_episodic=True)
+    _check_rollout(env, ora, 17)
+
+
+@pytest.mark.parametrize("episodic", [True, False])
+def test_rollout_stochastic_polarisation(B, O, episodic):
+    n = 6007
+    env = B.CellularVectorEnv(num_envs=n, stochastic=True, deadlock=True, env_seed=5, rng_episodic=episodic, max_episode_steps=9)
+    ora = O.OracleEnv(n_envs=n, noise=True, deadlock=True, seed=5, rng_episodic=episodic, max_episode_steps=9, reward="nonlinear_rp")
+    _check_rollout(env, ora, 13)
+    # ordinary steps continue from the state and the counters the rollout left behind
+    a = np.random.default_rng(0).integers(0, 3, (3, n)).astype(np.int8)
+    env.step_device(dev(a)); ora.step(a)
+    assert_matches_oracle(env, ora)
+
+
+def test_rollout_16_cells(B, O):
+    n = 3001
+    env = B.CellularVectorEnv(num_envs=n, n_cells=16, n_states=4, stochastic=True, env_seed=2, difficulty="hard")
+    ora = O.OracleEnv(n_envs=n, n_cells=16, n_states=4, noise=True, seed=2, rng_episodic=True, difficulty="hard", reward="nonlinear_rp")
+    _check_rollout(env, ora, 6)
+
+
+def test_rollout_gridworld_random_and_policy(B, O, golden_gw):
+    n = 20011
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=9, dispersal_prob=0.05, max_episode_steps=24)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=9, dispersal_prob=0.05, max_episode_steps=24)
+    _check_rollout(env, ora, 30)
+    env.check_actions()
+    # tabular policy: the reference's initial_policy (grid_world.py:423-438) as a 400-entry table
+    policy = np.zeros(400, np.int32)
+    st, pol = golden_gw["gw_states"].astype(int), golden_gw["gw_initial_policy"].astype(int)
+    policy[st[:, 0] + 20 * st[:, 1]] = pol[:, 0] + 5 * pol[:, 1]
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=10, max_episode_steps=16)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=10, max_episode_steps=16)
+    _check_rollout(env, ora, 20, policy=policy)
+
+
+def test_rollout_tabular_policy_polarisation(B, O):
+    n = 4099
+    policy = np.random.default_rng(4).integers(0, 27, 27).astype(np.int32)
+    env = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=3)
+    ora = O.OracleEnv(n_envs=n, noise=True, seed=3, rng_episodic=True, reward="nonlinear_rp")
+    _check_rollout(env, ora, 25, policy=policy)
