@@ -90,11 +90,6 @@ void gc_build_grid_lut(uint32_t *lut);
 void gc_build_pair_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut,
                        uint32_t *unsafe_rows);
 
-struct LaunchGeom {
-    int blocks_per_sm_hint;
-    int n_sm;
-};
-
 cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm,
                                 cudaStream_t stream);
 // fast path (S, A <= 4): lut = 1024 pair entries [fire_d][fire_c][s_c | a_c<<2 | s_d<<4 | a_d<<6] followed

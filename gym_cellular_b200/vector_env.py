@@ -24,7 +24,6 @@ import torch
 from . import _lib, tables
 from ._gym import gym
 
-GRID_INITIAL_CELLS = (15, 18)        # grid_world.py:238-259 through cellularize (:349-359)
 _FAMILIES = {
     # id suffix: (kind, n_cells, n_states, n_actions, stochastic)
     "Cells3States3Actions3-v0": ("cellular", 3, 3, 3, False),
