@@ -465,7 +465,7 @@ def main():
             "e2e": {**main_res["e2e"], "pcie_measured": measure_pcie(device)},
             "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
             "roofline": main_res["roofline"], "episode_stats": main_res["episode_stats"],
-            "fused_rollout": main_res["fused_rollout"],
+            "fused_rollout": main_res["fused_rollout"], "cuda_graph": main_res["cuda_graph"],
         }
         if extra:
             line["workloads"] = extra

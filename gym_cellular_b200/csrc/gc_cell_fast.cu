@@ -159,20 +159,40 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
-    const uint32_t step_counter = launch_step_counter(io);
+    const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? launch_step_counter(io) : 0u;
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;   // < 2^32 per thread and launch
     long long st_reward = 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
-    for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
-         e0 < io.end; e0 += stride) {
+    // Narrow envs (C < 4: a thread reads only ~10 words per 4 envs) prefetch the inputs of their next
+    // 4-env word before computing the current one, to keep enough bytes in flight per SM.
+    constexpr bool PREFETCH = NG == 0;
+    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+    uint32_t ps[4], pa[4];
+    int4 pt = make_int4(0, 0, 0, 0);
+    if constexpr (PREFETCH) if (e0 < io.end) {
+        load_cells<R>(io, 0, e0, ps, pa);
+        pt = ld_stream_v4(io.t + e0);
+    }
+    for (; e0 < io.end; e0 += stride) {
         const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);    // envs of this word in range
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);           // multiple of 4: | e never carries
         const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
 
         uint32_t sa[4], aa[4], sb[4], ab[4];
-        if (NG > 0) load_cells<4>(io, 0, e0, sa, aa); else load_cells<R>(io, 0, e0, sa, aa);
-        const int4 t4 = ld_stream_v4(io.t + e0);
-        if (NG > 1) load_cells<4>(io, 4, e0, sb, ab); else if (NG == 1 && R > 0) load_cells<R>(io, 4, e0, sb, ab);
+        int4 t4;
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sa[i] = ps[i]; aa[i] = pa[i]; }
+            t4 = pt;
+            if (e0 + stride < io.end) {
+                load_cells<R>(io, 0, e0 + stride, ps, pa);
+                pt = ld_stream_v4(io.t + e0 + stride);
+            }
+        } else {
+            load_cells<4>(io, 0, e0, sa, aa);
+            t4 = ld_stream_v4(io.t + e0);
+            if (NG > 1) load_cells<4>(io, 4, e0, sb, ab); else if (R > 0) load_cells<R>(io, 4, e0, sb, ab);
+        }
 
         const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
         int tn[kEPT] = {t4.x + 1, t4.y + 1, t4.z + 1, t4.w + 1};

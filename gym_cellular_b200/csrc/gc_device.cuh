@@ -28,7 +28,15 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, int e) { return (w >> (8 * e)) & 0xFFu; }
+// byte e of w, zero-extended
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int e)
+{
+#ifdef GC_BYTE_OF_PRMT
+    return __byte_perm(w, 0u, 0x4440u + static_cast<uint32_t>(e));   // one PRMT (bytes 4.. = the zero operand)
+#else
+    return (w >> (8 * e)) & 0xFFu;
+#endif
+}
 
 // streaming accesses: every byte is used once, keep it out of L1
 __device__ __forceinline__ uint32_t ld_stream_u32(const void *p)

@@ -29,13 +29,29 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     const int64_t ld = io.ld;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
-    for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
-         e0 < io.end; e0 += stride) {
+    // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
+    // reads 32 bytes per word, so without the prefetch too few bytes are in flight per SM to cover the
+    // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).
+    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+    uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;
+    int4 p_t = make_int4(0, 0, 0, 0);
+    if (e0 < io.end) {
+        p_s0 = ld_stream_u32(io.state + e0); p_s1 = ld_stream_u32(io.state + ld + e0);
+        p_a0 = ld_stream_u32(io.actions + e0); p_a1 = ld_stream_u32(io.actions + ld + e0);
+        p_t = ld_stream_v4(io.t + e0);
+    }
+    for (; e0 < io.end; e0 += stride) {
         const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
-        const uint32_t s0w = ld_stream_u32(io.state + e0), s1w = ld_stream_u32(io.state + ld + e0);
-        uint32_t a0w = ld_stream_u32(io.actions + e0), a1w = ld_stream_u32(io.actions + ld + e0);
-        const int4 t4 = ld_stream_v4(io.t + e0);
+        const uint32_t s0w = p_s0, s1w = p_s1;
+        uint32_t a0w = p_a0, a1w = p_a1;
+        const int4 t4 = p_t;
+        if (e0 + stride < io.end) {
+            const int64_t en = e0 + stride;
+            p_s0 = ld_stream_u32(io.state + en); p_s1 = ld_stream_u32(io.state + ld + en);
+            p_a0 = ld_stream_u32(io.actions + en); p_a1 = ld_stream_u32(io.actions + ld + en);
+            p_t = ld_stream_v4(io.t + en);
+        }
         const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
         // action codes above 4 mean "no position" like 4 (per-byte min(a, 4)); state codes are ours
         a0w = __vminu4(a0w, 0x04040404u);
