@@ -29,7 +29,13 @@ namespace {
 #endif
 // resident blocks per SM the register budget is sized for; the Philox variants of wide envs carry
 // 16 more registers (one random block per env) and get the budget of three blocks
-constexpr int pair_min_blocks(int c, int rng) { return (rng == GC_RNG_PHILOX && c > 4) ? 3 : GC_PAIR_MINB; }
+#ifndef GC_PAIR_MINB_NARROW
+#define GC_PAIR_MINB_NARROW GC_PAIR_MINB
+#endif
+constexpr int pair_min_blocks(int c, int rng)
+{
+    return (rng == GC_RNG_PHILOX && c > 4) ? 3 : (c < 4 ? GC_PAIR_MINB_NARROW : GC_PAIR_MINB);
+}
 
 // Everything a thread carries across the cell groups of its four envs.
 struct EnvAcc {

@@ -11,8 +11,12 @@
 namespace {
 
 
+#ifndef GC_GRID_MINB
+#define GC_GRID_MINB 4
+#endif
+
 template <int RNG>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, GC_GRID_MINB)
 grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ StepIO io)
 {
     __shared__ uint32_t s_lut[GC_GRID_LUT_ENTRIES];

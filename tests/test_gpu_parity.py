@@ -562,3 +562,59 @@ def test_rollout_tabular_policy_polarisation(B, O):
     env = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=3)
     ora = O.OracleEnv(n_envs=n, noise=True, seed=3, rng_episodic=True, reward="nonlinear_rp")
     _check_rollout(env, ora, 25, policy=policy)
+
+
+# ---------------------------------------------------------------------------------------------
+# Full BASELINE sizes against the oracle itself (all host cores), not only through properties
+
+def _threads():
+    import os
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+def _full_size_compare(env, ora, steps, gridworld=False):
+    n = env.num_envs
+    g = torch.Generator(device="cuda").manual_seed(123)
+    for _ in range(steps):
+        if gridworld:
+            a = torch.full((2, n), 4, dtype=torch.int8, device="cuda")
+            jur = torch.randint(0, 2, (n,), device="cuda", generator=g)
+            pos = torch.randint(0, 4, (n,), device="cuda", generator=g).to(torch.int8)
+            a[0] = torch.where(jur == 0, pos, a[0]); a[1] = torch.where(jur == 1, pos, a[1])
+        else:
+            a = torch.randint(0, env.n_actions, (env.n_cells, n), dtype=torch.int8, device="cuda", generator=g)
+        env.step_device(a)
+        ora.step_parallel(a.cpu().numpy(), _threads())
+    assert bool((env.state.cpu() == torch.from_numpy(ora.state)).all())
+    assert (host(env.tabular_state()) == ora.index).all()
+    assert (host(env.time_step) == ora.t).all()
+    assert (host(env._truncated[:n]) == ora.truncated).all() and (host(env._unsafe[:n]) == ora.unsafe).all()
+    assert (host(env._count[:n]) == ora.count).all()
+    np.testing.assert_allclose(host(env._reward[:n]), ora.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+
+
+def test_config3_full_size_vs_oracle(B, O):
+    n = 1 << 20
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=0, max_episode_steps=128, emit_side_effects=False)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=0, max_episode_steps=128)
+    _full_size_compare(env, ora, 12, gridworld=True)
+
+
+def test_config4_full_size_vs_oracle(B, O):
+    n = 1 << 24
+    env = B.CellularVectorEnv(num_envs=n, n_cells=16, n_states=4, emit_side_effects=False)
+    ora = O.OracleEnv(n_envs=n, n_cells=16, n_states=4)
+    _full_size_compare(env, ora, 2)
+
+
+def test_config5_mixed_shard_vs_oracle(B, O):
+    """One GPU's share of BASELINE config 5 at 8 GPUs: 4M stochastic polarisation + 4M grid-world envs,
+    global ids as rank 3 of 8 would own them."""
+    n = 1 << 22
+    off = 3 * (1 << 23)
+    pol = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=0, max_episode_steps=128, env_id_offset=off, emit_side_effects=False)
+    opol = O.OracleEnv(n_envs=n, noise=True, seed=0, rng_episodic=True, max_episode_steps=128, env_id_offset=off, reward="nonlinear_rp")
+    _full_size_compare(pol, opol, 3)
+    gw = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=0, max_episode_steps=128, env_id_offset=off + n, emit_side_effects=False)
+    ogw = O.OracleEnv(kind="gridworld", n_envs=n, seed=0, max_episode_steps=128, env_id_offset=off + n)
+    _full_size_compare(gw, ogw, 3, gridworld=True)
