@@ -128,6 +128,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+HOST_CHUNK_ENVS = 1 << 20
+
+
 def build_batches(workload, device, rank, n_override=None, env_scale=1.0):
     """Creates the vector envs of one rank and their pre-generated device action rings."""
     import torch
@@ -139,7 +142,7 @@ def build_batches(workload, device, rank, n_override=None, env_scale=1.0):
     for kind, frac, kw in w["parts"]:
         n = int(n_total * frac) // 16 * 16
         env = CellularVectorEnv(kind=kind, num_envs=n, device=device, env_seed=0, env_id_offset=offset,
-                                emit_side_effects=False, collect_stats=True, **kw)
+                                emit_side_effects=False, collect_stats=True, host_chunk_envs=HOST_CHUNK_ENVS, **kw)
         offset += n
         ring = []
         for _ in range(RING):
@@ -301,9 +304,11 @@ def cpu_baseline(workload, budget_s=12.0):
     threads = os.cpu_count() or 1
     rate, _, _ = time_oracle(workload, 1 << 16, 2, 1, threads)          # calibration
     n_sample = int(min(1 << 22, max(1 << 14, rate * budget_s / 8)))
-    rate, el, n = time_oracle(workload, n_sample, 8, 1, threads)
+    steps = 24
+    rate, el, n = time_oracle(workload, n_sample, steps, 1, threads)
     return {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": f"C oracle (oracle/gc_oracle.c), {n} envs x 8 steps of {workload}, {threads} threads, {el:.1f} s"}
+            "sample": f"C oracle (oracle/gc_oracle.c), {n} envs x {steps} steps of {workload}, {threads} threads, "
+                      f"{el:.1f} s wall = {el * threads:.0f} core-seconds"}
 
 
 def run_reference_arm(args, workload):
@@ -410,14 +415,18 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg2/cfg3/cfg5 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-chunk", type=int, default=None, help="envs per chunk of the host (e2e) path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.host_chunk:
+        global HOST_CHUNK_ENVS
+        HOST_CHUNK_ENVS = args.host_chunk
 
     if args.impl == "reference":
         run_reference_arm(args, args.workload)
