@@ -171,12 +171,16 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
     // Narrow envs (C < 4: a thread reads only ~10 words per 4 envs) prefetch the inputs of their next
     // 4-env word before computing the current one, to keep enough bytes in flight per SM.
-    constexpr bool PREFETCH = NG == 0;
+#ifndef GC_PAIR_PREFETCH_WIDE
+#define GC_PAIR_PREFETCH_WIDE 0
+#endif
+    constexpr bool PREFETCH = NG == 0 || GC_PAIR_PREFETCH_WIDE;
+    constexpr int G0 = NG > 0 ? 4 : R;                       // cells in the first group
     int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
     uint32_t ps[4], pa[4];
     int4 pt = make_int4(0, 0, 0, 0);
     if constexpr (PREFETCH) if (e0 < io.end) {
-        load_cells<R>(io, 0, e0, ps, pa);
+        load_cells<G0>(io, 0, e0, ps, pa);
         pt = ld_stream_v4(io.t + e0);
     }
     for (; e0 < io.end; e0 += stride) {
@@ -190,8 +194,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 4; ++i) { sa[i] = ps[i]; aa[i] = pa[i]; }
             t4 = pt;
+            if (NG > 1) load_cells<4>(io, 4, e0, sb, ab); else if (NG == 1 && R > 0) load_cells<R>(io, 4, e0, sb, ab);
             if (e0 + stride < io.end) {
-                load_cells<R>(io, 0, e0 + stride, ps, pa);
+                load_cells<G0>(io, 0, e0 + stride, ps, pa);
                 pt = ld_stream_v4(io.t + e0 + stride);
             }
         } else {

@@ -266,6 +266,28 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                 "count_sum": int(s[_lib.STAT_COUNT]), "episodes_truncated": int(s[_lib.STAT_TRUNCATED]),
                 "reward_sum": float(s[_lib.STAT_REWARD_Q24]) / 2.0 ** 24}
 
+    # ---- checkpoint / resume -----------------------------------------------------------------------
+    def state_dict(self):
+        """Everything needed to resume: the resident state, episode steps, statistics and the global
+        step (the RNG itself is stateless: Philox is keyed by seed, global env id and step)."""
+        self.sync_step_counter()
+        return {"state": self._state.clone(), "t": self._t.clone(),
+                "stats": None if self._stats is None else self._stats.clone(),
+                "global_step": int(self._lib.gc_get_global_step(self._h)),
+                "meta": (self.kind, self.num_envs, self.n_cells, self.n_states, self.env_seed, self.env_id_offset)}
+
+    def load_state_dict(self, sd):
+        if tuple(sd["meta"]) != (self.kind, self.num_envs, self.n_cells, self.n_states, self.env_seed, self.env_id_offset):
+            raise ValueError("state_dict belongs to a differently configured env")
+        self._state.copy_(sd["state"])
+        self._t.copy_(sd["t"])
+        if self._stats is not None and sd["stats"] is not None:
+            self._stats.copy_(sd["stats"])
+        _lib.check(self._lib.gc_set_global_step(self._h, int(sd["global_step"])))
+        # refresh the tabular index of the restored state
+        _lib.check(self._lib.gc_encode(self.device.index, self.num_envs, self.ld, self.n_cells, self.n_states,
+                                       _ptr(self._state), _ptr(self._index), self._stream()))
+
     @property
     def launch_count(self):
         return int(self._lib.gc_launch_count(self._h))

@@ -618,3 +618,84 @@ def test_config5_mixed_shard_vs_oracle(B, O):
     gw = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=0, max_episode_steps=128, env_id_offset=off + n, emit_side_effects=False)
     ogw = O.OracleEnv(kind="gridworld", n_envs=n, seed=0, max_episode_steps=128, env_id_offset=off + n)
     _full_size_compare(gw, ogw, 3, gridworld=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# Largest sizes, resume, DLPack, argument errors
+
+def test_config5_all_64m_envs_on_one_gpu(B, O):
+    """All 2^26 envs of BASELINE config 5 on a single GPU (32M stochastic polarisation + 32M grid
+    world), one step against the oracle plus global-id bookkeeping at the 2^25 boundary."""
+    n = 1 << 25
+    pol = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=0, max_episode_steps=128, emit_side_effects=False)
+    opol = O.OracleEnv(n_envs=n, noise=True, seed=0, rng_episodic=True, max_episode_steps=128, reward="nonlinear_rp")
+    _full_size_compare(pol, opol, 2)
+    del pol, opol
+    gw = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=0, max_episode_steps=128, env_id_offset=n, emit_side_effects=False)
+    ogw = O.OracleEnv(kind="gridworld", n_envs=n, seed=0, max_episode_steps=128, env_id_offset=n)
+    _full_size_compare(gw, ogw, 2, gridworld=True)
+
+
+def test_state_dict_resume(B):
+    n = 30000
+    rng = np.random.default_rng(0)
+    acts = [dev(rng.integers(0, 3, (3, n)).astype(np.int8)) for _ in range(12)]
+    env = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=6, rng_episodic=False, max_episode_steps=5)
+    for a in acts[:4]:
+        env.step_device(a)
+    sd = env.state_dict()
+    for a in acts[4:]:
+        env.step_device(a)
+    want_state, want_stats = env.state.clone(), env.stats()
+    env2 = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=6, rng_episodic=False, max_episode_steps=5)
+    env2.load_state_dict(sd)
+    assert bool((env2.tabular_state() == env2.tabularize(env2.state)).all())
+    for a in acts[4:]:
+        env2.step_device(a)
+    assert bool((env2.state == want_state).all()) and env2.stats() == want_stats
+    with pytest.raises(ValueError):
+        B.CellularVectorEnv(num_envs=n + 16, stochastic=True, env_seed=6).load_state_dict(sd)
+
+
+def test_dlpack_exchange(B):
+    """Device buffers cross framework boundaries over DLPack: actions come in as any __dlpack__ exporter,
+    observations go out as capsules."""
+    class Foreign:                                   # stands for a cupy / jax array
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None):
+            return self._t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+    n = 1024
+    env = B.CellularVectorEnv(num_envs=n)
+    a = torch.randint(0, 3, (3, n), dtype=torch.int8, device="cuda")
+    obs, rew, term, trunc, info = env.step(Foreign(a))
+    back = torch.from_dlpack(torch.utils.dlpack.to_dlpack(env.state))
+    assert back.data_ptr() == env.state.data_ptr() and bool((back == torch.sign(a)).all())
+    assert term.dtype == torch.bool and trunc.dtype == torch.bool and info["tabular_state"].dtype == torch.int32
+
+
+def test_argument_errors_on_gpu(B):
+    import ctypes as C
+    from gym_cellular_b200 import _lib
+    env = B.CellularVectorEnv(num_envs=100)
+    L, p = env._lib, lambda t: C.c_void_p(t.data_ptr())
+    args = (p(env._actions), p(env._state), p(env._t), p(env._reward), p(env._index), p(env._terminated),
+            p(env._truncated), p(env._unsafe), p(env._count), None, None, None, None)
+    assert L.gc_step(env._h, 8, 16, *args) == _lib.ERR_INVALID and b"multiple of 16" in L.gc_last_error()
+    assert L.gc_step(env._h, 0, 200, *args) == _lib.ERR_INVALID and b"outside" in L.gc_last_error()
+    assert L.gc_step(env._h, 0, 100, None, *args[1:]) == _lib.ERR_INVALID
+    assert L.gc_step(env._h, 0, 100, *args) == 0 and L.gc_step(env._h, 16, 84, *args) == 0     # ragged tail chunk
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(5, 100, dtype=torch.int8, device="cuda"))
+    with pytest.raises(_lib.GcError):
+        B.CellularVectorEnv(num_envs=16, n_cells=17)
+    with pytest.raises(_lib.GcError):
+        B.CellularVectorEnv(num_envs=16, n_cells=16, n_states=8)                                # 8^16 > 2^32
+    gw = B.CellularVectorEnv(kind="gridworld", num_envs=16)
+    assert L.gc_rollout(gw._h, 0, 0, None, p(gw._state), p(gw._t), p(gw._index), p(gw._reward), p(gw._index), None, None) == _lib.ERR_INVALID
+    with pytest.raises(_lib.GcError):
+        B.CellularVectorEnv(num_envs=16, n_cells=3, n_states=6, stochastic=True).rollout(3)     # fast path only
