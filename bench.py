@@ -334,6 +334,35 @@ def run_reference_arm(args, workload):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_near_gpu(device):
+    """Pin this rank's host threads (and hence its pinned staging buffers, by first touch) to the CPUs
+    of the GPU's NUMA node; matters for the host path when 8 ranks share the host.  Best effort."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device), "pci_bus_id") else None
+        if bdf is None:
+            import pynvml
+            pynvml.nvmlInit()
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device.index)).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cpus of the GPU's NUMA node"
+        return "no local cpu allowed"
+    except Exception as exc:           # pragma: no cover - depends on the box
+        return f"unbound ({type(exc).__name__})"
+
+
 def measured_peak():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -442,6 +471,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    affinity = bind_near_gpu(device) if world > 1 else "single rank: unbound"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -470,7 +500,8 @@ def main():
                        "parallelism": f"env-sharded x{world}, NCCL all-reduce of episode statistics once per iteration",
                        "l2": "per-step working set larger than L2" if not WORKLOADS[args.workload]["l2_resident"]
                              else "working set is L2-resident (launch-bound, not an HBM measurement)",
-                       "actions": f"ring of {RING} pre-generated device buffers, uniform random"},
+                       "actions": f"ring of {RING} pre-generated device buffers, uniform random",
+                       "host_affinity": affinity},
             "e2e": {**main_res["e2e"], "pcie_measured": measure_pcie(device)},
             "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
             "roofline": main_res["roofline"], "episode_stats": main_res["episode_stats"],
