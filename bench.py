@@ -338,14 +338,10 @@ def bind_near_gpu(device):
     """Pin this rank's host threads (and hence its pinned staging buffers, by first touch) to the CPUs
     of the GPU's NUMA node; matters for the host path when 8 ranks share the host.  Best effort."""
     try:
-        import torch
-        bdf = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(
-            torch.cuda.get_device_properties(device), "pci_bus_id") else None
-        if bdf is None:
-            import pynvml
-            pynvml.nvmlInit()
-            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device.index)).busId
-            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        import pynvml
+        pynvml.nvmlInit()
+        bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device.index)).busId
+        bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
         bdf = bdf.lower()
         if len(bdf.split(":")[0]) == 8:
             bdf = bdf[4:]
