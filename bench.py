@@ -300,6 +300,21 @@ def time_oracle(workload, n_sample, steps, warmup, threads):
     return sum(n for _, _, n in envs) * steps / el, el, sum(n for _, _, n in envs)
 
 
+def python_port_rate(workload):
+    """What the reference's own execution model (one Python object per env) costs on this box: the
+    pure-Python port oracle/pyport.py in a fresh process (fork pool over all cores).  Context only."""
+    part = next((kw for kind, _, kw in WORKLOADS[workload]["parts"] if kind == "cellular"), None)
+    if part is None:
+        return None
+    try:
+        out = subprocess.run([sys.executable, "-m", "oracle.pyport", "--envs", "64", "--steps", "150", "--cells",
+                              str(part["n_cells"]), "--levels", str(part["n_states"])], cwd=REPO, capture_output=True,
+                             text=True, timeout=120).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as exc:
+        return {"error": type(exc).__name__}
+
+
 def cpu_baseline(workload, budget_s=12.0):
     threads = os.cpu_count() or 1
     rate, _, _ = time_oracle(workload, 1 << 16, 2, 1, threads)          # calibration
@@ -308,7 +323,8 @@ def cpu_baseline(workload, budget_s=12.0):
     rate, el, n = time_oracle(workload, n_sample, steps, 1, threads)
     return {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
             "sample": f"C oracle (oracle/gc_oracle.c), {n} envs x {steps} steps of {workload}, {threads} threads, "
-                      f"{el:.1f} s wall = {el * threads:.0f} core-seconds"}
+                      f"{el:.1f} s wall = {el * threads:.0f} core-seconds",
+            "python_port": python_port_rate(workload)}
 
 
 def run_reference_arm(args, workload):

@@ -326,15 +326,15 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if isinstance(actions, np.ndarray) or (isinstance(actions, (tuple, list)) and len(actions)
                                                 and isinstance(actions[0], np.ndarray)):
             return self._step_host(actions)
-        self._load_actions_device(actions)
-        self.step_device(replay_u=replay_u)
+        self.step_device(actions, replay_u=replay_u)
         return self._v_obs, self._v_reward, self._v_term, self._v_trunc, self._v_infos
 
     def step_device(self, actions=None, replay_u=None):
         """Launch one step on the current stream; no host synchronisation, no output marshalling.
         `actions`: None = the env's own action buffer (`action_buffer`) already holds them."""
+        a_ptr = _ptr(self._actions)
         if actions is not None:
-            self._load_actions_device(actions)
+            a_ptr = self._load_actions_device(actions)
         ru = None
         if replay_u is not None:
             ru = torch.as_tensor(replay_u, dtype=torch.float64, device=self.device).contiguous()
@@ -342,7 +342,7 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             if ru.shape != (self.num_envs, slots):
                 raise ValueError(f"replay_u must have shape {(self.num_envs, slots)}")
         _lib.check(self._lib.gc_step(
-            self._h, 0, self.num_envs, _ptr(self._actions), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
+            self._h, 0, self.num_envs, a_ptr, _ptr(self._state), _ptr(self._t), _ptr(self._reward),
             _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
             _ptr(self._se_row), _ptr(ru), _ptr(self._stats), self._stream()))
 
@@ -436,8 +436,12 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             actions = actions.t()
         if actions.shape != (self.n_cells, self.num_envs):
             raise ValueError(f"actions must have shape {(self.n_cells, self.num_envs)}")
+        if (actions.dtype == torch.int8 and actions.device == self.device and actions.is_contiguous()
+                and self.num_envs == self.ld and actions.data_ptr() % 16 == 0):
+            return C.c_void_p(actions.data_ptr())       # the caller's tensor has the kernel's layout: no copy
         if actions.data_ptr() != self._actions.data_ptr():
             self._actions[:, :self.num_envs].copy_(actions.to(self.device, non_blocking=True))
+        return _ptr(self._actions)
 
     def _build_views(self):
         """Zero-copy views handed back by step()/reset(): they alias the env's buffers (valid until the

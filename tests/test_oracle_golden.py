@@ -188,3 +188,21 @@ def test_generalisation_reduces_to_reference_rules():
         ref.step(ac[[0, 1, j]])
         assert (wide.state[[0, 1, j]] == ref.state).all()
         assert (wide.se_row[[0, 1, j]] == ref.se_row).all()
+
+
+def test_python_port_matches_reference(golden_pol):
+    """oracle/pyport.py (the timing stand-in for the reference's Python step loop) against the golden vectors."""
+    from oracle.pyport import PolarisationEnv
+    g = golden_pol
+    names = np.array(["silent", "safe", "unsafe"])
+    for tag, C in (("c3", 3), ("c2", 2)):
+        env = PolarisationEnv(C, 3)
+        n_s = 3 ** C
+        for p in range(n_s * n_s):
+            s, a = detab([p // n_s], C, 3)[:, 0], detab([p % n_s], C, 3)[:, 0]
+            env.reset()
+            env.state = tuple(int(x) for x in s)
+            ns, r, term, trunc, info = env.step(tuple(int(x) for x in a))
+            assert ns == tuple(g[f"{tag}_next"][p]) and r == g[f"{tag}_reward_right_polarizing"][p]
+            assert (info["side_effects"] == names[g[f"{tag}_se_easy"][p]]).all()
+            assert env.data["side_effects_incidence"] == g[f"{tag}_incidence"][p]
