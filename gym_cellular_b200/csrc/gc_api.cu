@@ -31,6 +31,27 @@ int fail(int code, const char *fmt, ...)
 
 constexpr int kHostStreams = 3;
 
+// Entry points run on the handle's device but leave the caller's current device untouched (a torch
+// process may be driving several GPUs).
+class DeviceGuard {
+public:
+    explicit DeviceGuard(int device) : prev_(-1), err_(cudaSuccess)
+    {
+        err_ = cudaGetDevice(&prev_);
+        if (err_ == cudaSuccess && prev_ != device) err_ = cudaSetDevice(device); else prev_ = -1;
+    }
+    ~DeviceGuard() { if (prev_ >= 0) cudaSetDevice(prev_); }
+    cudaError_t error() const { return err_; }
+private:
+    int prev_;
+    cudaError_t err_;
+};
+
+#define GC_ON_DEVICE(dev)                                                                      \
+    DeviceGuard guard_(dev);                                                                   \
+    if (guard_.error() != cudaSuccess)                                                         \
+        return fail(GC_ERR_CUDA, "cannot switch to device %d: %s", (dev), cudaGetErrorString(guard_.error()))
+
 // x * 2^-32 < p  <=>  x < ceil(p * 2^32)   (p * 2^32 is exact in double: a power-of-two scaling)
 unsigned long long threshold_of(double p)
 {
@@ -160,7 +181,7 @@ int gc_create(const gc_config *cfg, gc_env **out)
     GC_CUDA(cudaGetDeviceCount(&n_dev));
     if (cfg->device < 0 || cfg->device >= n_dev)
         return fail(GC_ERR_INVALID, "device %d not in [0, %d)", cfg->device, n_dev);
-    GC_CUDA(cudaSetDevice(cfg->device));
+    GC_ON_DEVICE(cfg->device);
     gc_env *env = new (std::nothrow) gc_env();
     if (!env) return fail(GC_ERR_INVALID, "out of host memory");
     std::memset(env, 0, sizeof(*env));
@@ -198,7 +219,7 @@ int gc_create(const gc_config *cfg, gc_env **out)
 int gc_destroy(gc_env *env)
 {
     if (!env) return GC_OK;
-    cudaSetDevice(env->cfg.device);
+    DeviceGuard guard_(env->cfg.device);
     if (env->host_ready)
         for (int i = 0; i < kHostStreams; ++i) {
             cudaStreamDestroy(env->hstream[i]);
@@ -269,7 +290,7 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         gc_build_pair_lut(t, C, S, A, noise, lut, &tab.unsafe_rows);
         uint32_t p4 = 1;
         for (int i = 0; i < 4; ++i) { tab.place4[i] = p4; p4 *= (uint32_t)S; }
-        GC_CUDA(cudaSetDevice(env->cfg.device));
+        GC_ON_DEVICE(env->cfg.device);
         if (!env->d_pair_lut) GC_CUDA(cudaMalloc(&env->d_pair_lut, sizeof(lut)));
         GC_CUDA(cudaMemcpy(env->d_pair_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     }
@@ -282,7 +303,7 @@ int gc_set_global_step(gc_env *env, int64_t step)
     if (int rc = check_env(env)) return rc;
     env->global_step = step;
     const uint32_t v = static_cast<uint32_t>(step);
-    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_ON_DEVICE(env->cfg.device);
     GC_CUDA(cudaMemcpy(env->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));   // synchronous: rare, control path
     return GC_OK;
 }
@@ -294,7 +315,7 @@ int64_t gc_get_global_step(const gc_env *env) { return env ? env->global_step : 
 int gc_sync_global_step(gc_env *env, void *stream)
 {
     if (int rc = check_env(env)) return rc;
-    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_ON_DEVICE(env->cfg.device);
     uint32_t v = 0;
     GC_CUDA(cudaMemcpyAsync(&v, env->d_step, sizeof(v), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
     GC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
@@ -309,7 +330,7 @@ int gc_reset(gc_env *env, const uint8_t *mask, int8_t *state, int32_t *t, uint32
     if (int rc = check_env(env)) return rc;
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     if (!state || !t) return fail(GC_ERR_INVALID, "state/t is NULL");
-    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_ON_DEVICE(env->cfg.device);
     int8_t init[GC_MAX_CELLS] = {0};
     uint32_t init_index;
     if (env->cfg.kind == GC_KIND_GRIDWORLD) {
@@ -337,7 +358,7 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
     if (!actions || !state || !t || !reward || !index || !terminated || !truncated || !unsafe || !count)
         return fail(GC_ERR_INVALID, "a required device pointer is NULL");
     if (int rc = check_range(env, env_begin, env_count)) return rc;
-    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_ON_DEVICE(env->cfg.device);
     StepIO io = make_io(env, env_begin, env_count, actions, state, t, reward, index, terminated,
                         truncated, unsafe, count, se_row, replay_u, stats);
     const bool full = env_begin == 0 && env_count == env->cfg.n_envs;
@@ -368,7 +389,7 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
     if (!h_actions || !d_actions || !d_state || !d_t || !d_reward || !d_index || !d_terminated ||
         !d_truncated || !d_unsafe || !d_count)
         return fail(GC_ERR_INVALID, "a required pointer is NULL");
-    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_ON_DEVICE(env->cfg.device);
     if (!env->host_ready) {
         for (int i = 0; i < kHostStreams; ++i) {
             GC_CUDA(cudaStreamCreateWithFlags(&env->hstream[i], cudaStreamNonBlocking));
@@ -419,7 +440,7 @@ int gc_rollout(gc_env *env, int32_t n_steps, int32_t policy_kind, const int32_t 
     if (policy_kind == GC_POLICY_TABLE && !policy) return fail(GC_ERR_INVALID, "GC_POLICY_TABLE needs a policy table");
     if (env->cfg.kind == GC_KIND_CELLULAR && !env->fast_ok)
         return fail(GC_ERR_INVALID, "gc_rollout supports the cellular family with n_states, n_actions <= 4 only");
-    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_ON_DEVICE(env->cfg.device);
     RolloutIO io;
     io.state = state; io.t = t; io.index = index; io.ret = ret; io.n_unsafe = n_unsafe; io.policy = policy;
     io.stats = reinterpret_cast<unsigned long long *>(stats);
@@ -449,7 +470,7 @@ int gc_rollout(gc_env *env, int32_t n_steps, int32_t policy_kind, const int32_t 
 int gc_poll_status(gc_env *env, void *stream)
 {
     if (int rc = check_env(env)) return rc;
-    GC_CUDA(cudaSetDevice(env->cfg.device));
+    GC_ON_DEVICE(env->cfg.device);
     unsigned long long word = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GC_CUDA(cudaMemcpyAsync(&word, env->d_status, sizeof(word), cudaMemcpyDeviceToHost, st));
@@ -466,7 +487,7 @@ int gc_encode(int device, int64_t n, int64_t ld, int32_t n_cells, int32_t radix,
 {
     if (!cells || !index || n < 0 || ld < n || ld % 16 != 0 || n_cells < 1 || radix < 1)
         return fail(GC_ERR_INVALID, "gc_encode: bad arguments");
-    GC_CUDA(cudaSetDevice(device));
+    GC_ON_DEVICE(device);
     cudaError_t e = gc_launch_encode((n + 3) / 4 * 4, ld, n_cells, (uint32_t)radix, cells, index,
                                      static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(GC_ERR_CUDA, "encode kernel launch failed: %s", cudaGetErrorString(e));
@@ -478,7 +499,7 @@ int gc_decode(int device, int64_t n, int64_t ld, int32_t n_cells, int32_t radix,
 {
     if (!cells || !index || n < 0 || ld < n || ld % 16 != 0 || n_cells < 1 || radix < 1)
         return fail(GC_ERR_INVALID, "gc_decode: bad arguments");
-    GC_CUDA(cudaSetDevice(device));
+    GC_ON_DEVICE(device);
     cudaError_t e = gc_launch_decode((n + 3) / 4 * 4, ld, n_cells, (uint32_t)radix, index, cells,
                                      static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(GC_ERR_CUDA, "decode kernel launch failed: %s", cudaGetErrorString(e));

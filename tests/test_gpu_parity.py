@@ -699,3 +699,24 @@ def test_argument_errors_on_gpu(B):
     assert L.gc_rollout(gw._h, 0, 0, None, p(gw._state), p(gw._t), p(gw._index), p(gw._reward), p(gw._index), None, None) == _lib.ERR_INVALID
     with pytest.raises(_lib.GcError):
         B.CellularVectorEnv(num_envs=16, n_cells=3, n_states=6, stochastic=True).rollout(3)     # fast path only
+
+
+def test_second_device_leaves_current_device_alone(B, O):
+    """A handle on cuda:1 runs there without changing the caller's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    assert torch.cuda.current_device() == 0
+    n = 5000
+    env = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=1, device="cuda:1")
+    ora = O.OracleEnv(n_envs=n, noise=True, seed=1, rng_episodic=True, reward="nonlinear_rp")
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        a = rng.integers(0, 3, (3, n)).astype(np.int8)
+        env.step(torch.from_numpy(a).to("cuda:1"))
+        ora.step(a)
+        assert torch.cuda.current_device() == 0
+    assert env.state.device.index == 1
+    assert_matches_oracle(env, ora)
+    obs, rew, *_ = env.step(a)                        # host path on the second device
+    ora.step(a)
+    assert (np.stack(obs) == ora.state).all() and torch.cuda.current_device() == 0
