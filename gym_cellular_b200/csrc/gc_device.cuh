@@ -116,15 +116,15 @@ __device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigne
 
 // ---------------------------------------------------------------------------------------------
 // Launch geometry: one wave of resident blocks (SM count x occupancy), grid-stride inside.
-template <auto Kernel>
+template <auto Kernel, int THREADS = kThreads>
 int grid_for(int64_t n_envs, int n_sm)
 {
     const auto kernel = Kernel;
     static int per_sm = 0;               // one static per kernel instantiation: query the occupancy once
     if (per_sm == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1))
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, 0) != cudaSuccess || per_sm < 1))
         per_sm = 1;
-    const int64_t need = (n_envs + kThreads * kEPT - 1) / (kThreads * kEPT);
+    const int64_t need = (n_envs + THREADS * kEPT - 1) / (THREADS * kEPT);
     const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;
     return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
 }

@@ -11,12 +11,18 @@
 namespace {
 
 
-#ifndef GC_GRID_MINB
-#define GC_GRID_MINB 4
+// One fat block per SM: the 40 KB table is staged once per SM instead of once per 256 threads, which
+// matters for launches of a few million envs where staging traffic rivals the useful traffic.
+#ifndef GC_GRID_THREADS
+#define GC_GRID_THREADS 1024
 #endif
+#ifndef GC_GRID_MINB
+#define GC_GRID_MINB 1
+#endif
+constexpr int kGridThreads = GC_GRID_THREADS;
 
 template <int RNG>
-__global__ void __launch_bounds__(kThreads, GC_GRID_MINB)
+__global__ void __launch_bounds__(kGridThreads, GC_GRID_MINB)
 grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ StepIO io)
 {
     __shared__ uint32_t s_lut[GC_GRID_LUT_ENTRIES];
@@ -24,7 +30,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (int i = threadIdx.x; i < GC_GRID_LUT_ENTRIES / 4; i += kThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < GC_GRID_LUT_ENTRIES / 4; i += kGridThreads) dst[i] = src[i];
     }
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
@@ -32,11 +38,11 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     const uint32_t step_counter = launch_step_counter(io);
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     const int64_t ld = io.ld;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
     // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
     // reads 32 bytes per word, so without the prefetch too few bytes are in flight per SM to cover the
     // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).
-    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x) * kEPT;
     uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;
     int4 p_t = make_int4(0, 0, 0, 0);
     if (e0 < io.end) {
@@ -182,8 +188,8 @@ cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_
 {
     const int64_t n = io.end - io.begin;
     if (rng_mode == GC_RNG_REPLAY)
-        grid_step_kernel<GC_RNG_REPLAY><<<grid_for<grid_step_kernel<GC_RNG_REPLAY>>(n, n_sm), kThreads, 0, st>>>(gp, io);
+        grid_step_kernel<GC_RNG_REPLAY><<<grid_for<grid_step_kernel<GC_RNG_REPLAY>, kGridThreads>(n, n_sm), kGridThreads, 0, st>>>(gp, io);
     else
-        grid_step_kernel<GC_RNG_PHILOX><<<grid_for<grid_step_kernel<GC_RNG_PHILOX>>(n, n_sm), kThreads, 0, st>>>(gp, io);
+        grid_step_kernel<GC_RNG_PHILOX><<<grid_for<grid_step_kernel<GC_RNG_PHILOX>, kGridThreads>(n, n_sm), kGridThreads, 0, st>>>(gp, io);
     return cudaGetLastError();
 }
