@@ -13,9 +13,11 @@ from .envs import (Cells3States3Actions3Env, Cells2Rest3Env, Cells3ResetVDeadloc
                    DebugEnv, DeepPlanningDebugEnv, DeepExplorationDebugEnv, PriorKnowledge,
                    GridWorldPriorKnowledge)
 from . import registration  # noqa: F401  (registers the gym_cellular/<Name>-v0 ids)
+from .alias import install_alias
 
 __all__ = ["CellularVectorEnv", "make_vector_env", "tables", "right_polarizing", "multiple_optima",
            "nonlinear", "nonlinear_right_polarizing", "Cells3States3Actions3Env", "Cells2Rest3Env",
            "Cells3ResetVDeadlockEnv", "GridWorldEnv", "PriorKnowledge", "GridWorldPriorKnowledge",
-           "generalized_cellular2tabular", "generalized_tabular2cellular", "cellular2tabular", "tabular2cellular"]
+           "generalized_cellular2tabular", "generalized_tabular2cellular", "cellular2tabular", "tabular2cellular",
+           "DebugEnv", "DeepPlanningDebugEnv", "DeepExplorationDebugEnv", "install_alias"]
 __version__ = "0.1.0"

@@ -78,3 +78,26 @@ def test_host_codec(golden_pol):
 def test_reward_callables_match_reference(golden_pol):
     assert B.right_polarizing((1, 1, 1), (2, 2, 2), None) == 0.8999999999999999
     assert B.nonlinear((1, 1, 1), (2, 2, 2), None) == 0.8073549220576041
+
+
+def test_install_alias_keeps_reference_imports_working():
+    import subprocess
+    import sys
+    code = (
+        "import gym_cellular_b200 as b; b.install_alias()\n"
+        "import gym_cellular\n"
+        "from gym_cellular.envs import Cells3States3Actions3Env, GridWorldEnv, generalized_cellular2tabular\n"
+        "from gym_cellular.envs.cells3states3actions3 import right_polarizing, nonlinear\n"
+        "from gym_cellular.envs.cells3resetVdeadlock import nonlinear as nl_rp\n"
+        "from gym_cellular.envs.utils.generalized_space_transformations import generalized_tabular2cellular\n"
+        "from gym_cellular.envs.grid_world import PriorKnowledge\n"
+        "from gym_cellular.envs.debug import DeepPlanningDebugEnv\n"
+        "import gymnasium\n"
+        "e = gymnasium.make('gym_cellular/Cells2Rest3-v0')\n"
+        "assert right_polarizing((1, 1, 1), (2, 2, 2), None) == 0.8999999999999999\n"
+        "assert abs(nl_rp((1, 1, 1), (2, 2, 2), None) - 0.9259994185562231) < 1e-12\n"
+        "assert generalized_tabular2cellular(5, [range(3)] * 3) == [2, 1, 0] and PriorKnowledge().n_states == 400\n"
+        "print('alias ok')\n")
+    env = dict(__import__("os").environ, PYTHONPATH=__import__("conftest").REPO)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0 and "alias ok" in out.stdout, out.stderr[-800:]
