@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <new>
 
 #include "gc_internal.h"
@@ -182,11 +183,13 @@ int gc_create(const gc_config *cfg, gc_env **out)
     if (cfg->device < 0 || cfg->device >= n_dev)
         return fail(GC_ERR_INVALID, "device %d not in [0, %d)", cfg->device, n_dev);
     GC_ON_DEVICE(cfg->device);
+    int n_sm = 0;
+    GC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     gc_env *env = new (std::nothrow) gc_env();
     if (!env) return fail(GC_ERR_INVALID, "out of host memory");
     std::memset(env, 0, sizeof(*env));
     env->cfg = *cfg;
-    GC_CUDA(cudaDeviceGetAttribute(&env->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    env->n_sm = n_sm;
     env->grid.dispersal_thr = threshold_of(cfg->dispersal_prob);
     env->grid.dispersal_thr_nz = env->grid.dispersal_thr != 0ull;
     env->grid.dispersal_thr_m1 = env->grid.dispersal_thr_nz ? static_cast<uint32_t>(env->grid.dispersal_thr - 1ull) : 0u;
@@ -199,11 +202,14 @@ int gc_create(const gc_config *cfg, gc_env **out)
         env->d_done = env->d_step + 1;
     }
     if (e == cudaSuccess && cfg->kind == GC_KIND_GRIDWORLD) {
-        static uint32_t lut[GC_GRID_LUT_ENTRIES];
-        gc_build_grid_lut(lut);
+        std::unique_ptr<uint32_t[]> lut(new (std::nothrow) uint32_t[GC_GRID_LUT_ENTRIES]);
         uint32_t *d_lut = nullptr;
-        e = cudaMalloc(&d_lut, sizeof(lut));
-        if (e == cudaSuccess) e = cudaMemcpy(d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+        if (!lut) e = cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) {
+            gc_build_grid_lut(lut.get());
+            e = cudaMalloc(&d_lut, GC_GRID_LUT_ENTRIES * sizeof(uint32_t));
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(d_lut, lut.get(), GC_GRID_LUT_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice);
         env->grid.lut = d_lut;
     }
     if (e != cudaSuccess) {
@@ -286,7 +292,7 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
             env->fast_ok = false;
     if (env->fast_ok) {
-        static uint2 lut[GC_PAIR_LUT_ENTRIES];
+        uint2 lut[GC_PAIR_LUT_ENTRIES];                       // 8.4 KB, on the stack: handles may be set up concurrently
         gc_build_pair_lut(t, C, S, A, noise, lut, &tab.unsafe_rows);
         uint32_t p4 = 1;
         for (int i = 0; i < 4; ++i) { tab.place4[i] = p4; p4 *= (uint32_t)S; }

@@ -156,13 +156,36 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         sp = gym.spaces
         self.single_observation_space = sp.Tuple([sp.Discrete(self.n_states) for _ in range(Cn)])
         self.single_action_space = sp.Tuple([sp.Discrete(self.n_actions) for _ in range(Cn)])
-        self.observation_space = sp.Tuple(
-            [sp.MultiDiscrete(np.full(self.num_envs, self.n_states)) for _ in range(Cn)])
-        self.action_space = sp.Tuple(
-            [sp.MultiDiscrete(np.full(self.num_envs, self.n_actions)) for _ in range(Cn)])
+        self._batched_spaces = None          # built on first access: 2 x n_cells arrays of num_envs int64
         self.closed = False
         self._build_views()
         self.reset()
+
+    def _spaces(self):
+        if self._batched_spaces is None:
+            sp = gym.spaces
+            self._batched_spaces = tuple(
+                sp.Tuple([sp.MultiDiscrete(np.full(self.num_envs, k)) for _ in range(self.n_cells)])
+                for k in (self.n_states, self.n_actions))
+        return self._batched_spaces
+
+    @property
+    def observation_space(self):
+        """Batched space (gymnasium convention: a Tuple of n_cells MultiDiscrete([n_states] * num_envs));
+        built lazily -- at 2^24 envs it is gigabytes of metadata nobody on the hot path needs."""
+        return self._spaces()[0]
+
+    @observation_space.setter
+    def observation_space(self, value):
+        pass                                   # gymnasium.vector.VectorEnv's class attribute protocol
+
+    @property
+    def action_space(self):
+        return self._spaces()[1]
+
+    @action_space.setter
+    def action_space(self, value):
+        pass
 
     # ------------------------------------------------------------------------------------------
     def _set_tables(self):
