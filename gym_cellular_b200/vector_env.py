@@ -222,11 +222,18 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         """int8 [n_cells, num_envs] view of the resident state (assignable through set_state)."""
         return self._state[:, :self.num_envs]
 
-    def set_state(self, cells, t=None):
+    def set_state(self, cells, t=None, validate=True):
+        """Overwrite the resident state (and optionally the episode steps), as tests and agents do with
+        `env.state = ...` on the reference; the tabular index is refreshed.  `validate` checks the level
+        range (one host synchronisation)."""
         cells = torch.as_tensor(cells, device=self.device).to(torch.int8).reshape(self.n_cells, self.num_envs)
+        if validate and (bool((cells < 0).any()) or bool((cells >= self.n_states).any())):
+            raise ValueError(f"state levels must lie in [0, {self.n_states})")
         self._state[:, :self.num_envs].copy_(cells)
         if t is not None:
             self._t[:self.num_envs].copy_(torch.as_tensor(t, device=self.device).to(torch.int32))
+        _lib.check(self._lib.gc_encode(self.device.index, self.num_envs, self.ld, self.n_cells, self.n_states,
+                                       _ptr(self._state), _ptr(self._index), self._stream()))
 
     def tabular_state(self, dtype=torch.int64):
         """Tabular index of the current observation (uint32 payload widened to `dtype`)."""

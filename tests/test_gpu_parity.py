@@ -691,6 +691,10 @@ def test_argument_errors_on_gpu(B):
     assert L.gc_step(env._h, 0, 100, *args) == 0 and L.gc_step(env._h, 16, 84, *args) == 0     # ragged tail chunk
     with pytest.raises(ValueError):
         env.step(torch.zeros(5, 100, dtype=torch.int8, device="cuda"))
+    with pytest.raises(ValueError, match="levels"):
+        env.set_state(np.full((3, 100), 3, np.int8))
+    env.set_state(np.full((3, 100), 2, np.int8))
+    assert (host(env.tabular_state()) == 26).all()
     with pytest.raises(_lib.GcError):
         B.CellularVectorEnv(num_envs=16, n_cells=17)
     with pytest.raises(_lib.GcError):
