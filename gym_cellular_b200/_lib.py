@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libgymcellular_b200.so")
 
 ABI_VERSION = 1
 KIND_CELLULAR, KIND_GRIDWORLD = 0, 1
-F_NOISE, F_RNG_EPISODIC, F_REWARD_LOG2 = 1, 4, 16
+F_NOISE, F_RNG_EPISODIC, F_REWARD_LOG2, F_GENERIC_KERNEL = 1, 4, 16, 32
 MAX_CELLS, MAX_LEVELS, N_STATS = 16, 8, 8
 STAT_STEPS, STAT_UNSAFE, STAT_COUNT, STAT_TRUNCATED, STAT_REWARD_Q24 = range(5)
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_ACTION = 0, -1, -2, -3, -4

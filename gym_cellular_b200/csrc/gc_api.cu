@@ -287,7 +287,7 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     tab.noise_thr_m1 = tab.noise_thr_nz ? static_cast<uint32_t>(tab.noise_thr - 1ull) : 0u;
 
     // ---- fast path: pair table (gc_cell_fast.cu) -------------------------------------------------
-    env->fast_ok = S <= 4 && A <= 4;
+    env->fast_ok = S <= 4 && A <= 4 && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
     for (int j = 3; j < C && env->fast_ok; ++j)
         if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
             env->fast_ok = false;

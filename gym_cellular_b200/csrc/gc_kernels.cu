@@ -21,15 +21,20 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// Cellular (polarisation family) step: C cells, per-cell identical [S][A] tables.
-template <int C, int RNG>
-__global__ void __launch_bounds__(kThreads)
+// Generic cellular step: any table set with up to GC_MAX_LEVELS levels / actions and per-cell side-effect
+// tables (the fast pair-table kernel of gc_cell_fast.cu covers n_states, n_actions <= 4 with equal tables
+// for the cells j >= 2).  One rolled loop over the cells; the row words of cell c+1 are requested before
+// cell c is computed; per (env, cell) one 64-bit shared load for the (level, action) entry, one for the
+// side-effect code.  ~50 registers, so eight blocks of 256 threads stay resident per SM.
+template <int RNG>
+__global__ void __launch_bounds__(kThreads, 4)
 cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ StepIO io)
 {
     __shared__ uint2 s_sa[GC_TBL];                 // .x packed move/noisy/draws, .y reward bits
     __shared__ float s_rn[GC_TBL];                 // reward when the draw fired
-    __shared__ uint8_t s_se[C][GC_TBL];
+    __shared__ uint8_t s_se[GC_MAX_CELLS][GC_TBL];
     __shared__ unsigned long long s_stats[5];
+    const int C = tab.n_cells;
 
     for (int i = threadIdx.x; i < GC_TBL; i += kThreads)
         s_sa[i] = make_uint2(tab.sa[i], __float_as_uint(tab.reward[i])), s_rn[i] = tab.reward_noisy[i];
@@ -38,105 +43,120 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
-    const uint32_t step_counter = launch_step_counter(io);
-    ThreadStats ts = {0, 0, 0, 0, 0};
+    const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? launch_step_counter(io) : 0u;
+    uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
+    long long st_reward = 0;
     const int64_t ld = io.ld;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
     for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
          e0 < io.end; e0 += stride) {
-        uint32_t sw[C], aw[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            sw[c] = ld_stream_u32(io.state + c * ld + e0);
-            aw[c] = ld_stream_u32(io.actions + c * ld + e0);
-        }
+        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
+        const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
+        uint32_t sw = ld_stream_u32(io.state + e0), aw = ld_stream_u32(io.actions + e0);
         const int4 t4 = ld_stream_v4(io.t + e0);
         const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
+        int tn[kEPT] = {t4.x + 1, t4.y + 1, t4.z + 1, t4.w + 1};
+        uint32_t trunc_w = 0, keep = 0xFFFFFFFFu;
+        if (io.max_episode_steps > 0) {
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                if (tn[e] >= io.max_episode_steps) { tn[e] = 0; trunc_w |= 1u << (8 * e); keep &= ~(0xFFu << (8 * e)); }
+        }
+        float r[kEPT] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t idx[kEPT] = {0, 0, 0, 0};
+        uint32_t unsafe_w = 0, count_w = 0, row0 = 0;        // row0: next levels of cell 0 (byte lanes)
+        uint32_t rnd[kEPT][4];
 
-        uint32_t nsw[C], sew[C];
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            uint32_t sn = 0, an = 0;
+            if (c + 1 < C) {                                  // prefetch the next cell's rows
+                sn = ld_stream_u32(io.state + (c + 1) * ld + e0);
+                an = ld_stream_u32(io.actions + (c + 1) * ld + e0);
+            }
+            if (RNG == GC_RNG_PHILOX && (c & 3) == 0) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) { nsw[c] = 0; sew[c] = 0; }
-        int tout[kEPT];
-        float rout[kEPT];
-        uint32_t iout[kEPT];
-        uint32_t trunc_w = 0, unsafe_w = 0, count_w = 0;
-
+                for (int e = 0; e < kEPT; ++e) {
+                    const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
+                    philox4x32_10(gid_lo | e, gid_hi, ctr, static_cast<uint32_t>(c >> 2), io.round_key, rnd[e]);
+                }
+            }
+            uint32_t row = 0, sew = 0;
 #pragma unroll
-        for (int e = 0; e < kEPT; ++e) {
-            const bool valid = (e0 + e) < io.end;
-            uint32_t ns[C];
-            float r = 0.0f;
-            uint32_t rnd[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const uint32_t s = byte_of(sw[c], e), a = byte_of(aw[c], e);
-                const uint32_t sa_ix = (s * GC_LVL_PAD + a) & (GC_TBL - 1);
+            for (int e = 0; e < kEPT; ++e) {
+                const uint32_t sa_ix = (byte_of(sw, e) * GC_LVL_PAD + byte_of(aw, e)) & (GC_TBL - 1);
                 const uint2 ent = s_sa[sa_ix];
-                uint32_t nxt = ent.x & 15u;
                 bool fire = false;
                 if (RNG == GC_RNG_PHILOX) {
-                    if ((c & 3) == 0) {
-                        const uint64_t gid = static_cast<uint64_t>(io.env_id_offset + e0 + e);
-                        const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
-                        philox4x32_10(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), ctr,
-                                      static_cast<uint32_t>(c >> 2), io.round_key, rnd);
-                    }
-                    fire = (ent.x & 0x100u) && (static_cast<unsigned long long>(rnd[c & 3]) < tab.noise_thr);
+                    const uint32_t word = (c & 3) == 0 ? rnd[e][0] : (c & 3) == 1 ? rnd[e][1] : (c & 3) == 2 ? rnd[e][2] : rnd[e][3];
+                    fire = (ent.x & 0x100u) && tab.noise_thr_nz && word <= tab.noise_thr_m1;
                 } else if (RNG == GC_RNG_REPLAY) {
-                    if (valid && (ent.x & 0x100u)) fire = io.replay[(e0 + e) * C + c] < tab.noise_prob;
+                    if (e < rem && (ent.x & 0x100u)) fire = io.replay[(e0 + e) * C + c] < tab.noise_prob;
                 }
-                if (fire) nxt = (ent.x >> 4) & 15u;
-                r += fire ? s_rn[sa_ix] : __uint_as_float(ent.y);             // left to right, from 0.0
-                ns[c] = nxt;
+                const uint32_t nxt = fire ? ((ent.x >> 4) & 15u) : (ent.x & 15u);
+                r[e] += fire ? s_rn[sa_ix] : __uint_as_float(ent.y);          // cell order, from 0.0
+                row |= nxt << (8 * e);
+                count_w += ((tab.counted_mask >> nxt) & 1u) << (8 * e);
             }
-            if (tab.reward_log2) r = log1pf(r) * 1.44269504088896341f;
+            if (c == 0) row0 = row;
+            // row 0 of the side-effects matrix: entry j from (s'_0, s'_p), p = 1 for j = 0 and p = j
+            // otherwise, so entry 0 is evaluated together with cell 1 (or with cell 0 itself if C == 1)
+            uint32_t sew0 = 0;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                const uint32_t s0n = byte_of(row0, e), sp = byte_of(row, e);
+                if (c > 0) {
+                    const uint32_t code = s_se[c][(s0n * GC_LVL_PAD + sp) & (GC_TBL - 1)];
+                    sew |= code << (8 * e);
+                    unsafe_w |= (code == 2u ? 1u : 0u) << (8 * e);
+                }
+                if (c == 1 || C == 1) {
+                    const uint32_t code0 = s_se[0][(s0n * GC_LVL_PAD + sp) & (GC_TBL - 1)];
+                    sew0 |= code0 << (8 * e);
+                    unsafe_w |= (code0 == 2u ? 1u : 0u) << (8 * e);
+                }
+            }
+            if (io.se_row) {
+                if (c > 0) st_stream_u32(io.se_row + c * ld + e0, sew);
+                if (c == 1 || C == 1) st_stream_u32(io.se_row + e0, sew0);
+            }
+            const uint32_t out = (row & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c])) & ~keep);
+            st_stream_u32(io.state + c * ld + e0, out);
+            const uint32_t place = tab.place[c];
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) idx[e] += byte_of(out, e) * place;
+            sw = sn; aw = an;
+        }
 
-            // row 0 of the side-effects matrix: entry j from (s'_0, s'_p), p = 1 for j = 0
-            uint32_t uns = 0, cnt = 0, idx = 0;
-            uint32_t code[C];
+        float rout[kEPT];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const uint32_t partner = (c == 0) ? ns[C > 1 ? 1 : 0] : ns[c];
-                code[c] = s_se[c][(ns[0] * GC_LVL_PAD + partner) & (GC_TBL - 1)];
-                uns |= (code[c] == 2u);
-                cnt += (tab.counted_mask >> ns[c]) & 1u;
-                idx += ns[c] * tab.place[c];
-            }
-            int tn = tin[e] + 1;
-            uint32_t tr = 0;
-            if (io.max_episode_steps > 0 && tn >= io.max_episode_steps) {   // fused time-limit auto-reset
-                tr = 1; tn = 0; idx = tab.init_index;
-#pragma unroll
-                for (int c = 0; c < C; ++c) ns[c] = static_cast<uint32_t>(tab.init[c]);
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                nsw[c] |= ns[c] << (8 * e);
-                sew[c] |= code[c] << (8 * e);
-            }
-            tout[e] = tn; rout[e] = r; iout[e] = idx;
-            trunc_w |= tr << (8 * e); unsafe_w |= uns << (8 * e); count_w |= cnt << (8 * e);
-            if (valid) {
-                ts.steps += 1; ts.unsafe += uns; ts.count += cnt; ts.truncated += tr;
-                ts.reward_q24 += __float2ll_rn(r * 16777216.0f);
-            }
+        for (int e = 0; e < kEPT; ++e) {
+            float rr = r[e];
+            if (tab.reward_log2) rr = log1pf(rr) * 1.44269504088896341f;
+            rout[e] = rr;
+            if (e < rem) st_reward += __float2int_rn(rr * 16777216.0f);
         }
-#pragma unroll
-        for (int c = 0; c < C; ++c) st_stream_u32(io.state + c * ld + e0, nsw[c]);
-        if (io.se_row) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) st_stream_u32(io.se_row + c * ld + e0, sew[c]);
+        {
+            const uint32_t vb = valid_bytes(rem);
+            st_steps += rem;
+            st_unsafe = add_bytes(unsafe_w & vb, st_unsafe);
+            st_count = add_bytes(count_w & vb, st_count);
+            st_trunc = add_bytes(trunc_w & vb, st_trunc);
         }
-        st_stream_v4(io.t + e0, make_int4(tout[0], tout[1], tout[2], tout[3]));
+        st_stream_v4(io.t + e0, make_int4(tn[0], tn[1], tn[2], tn[3]));
         st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
                                                __float_as_int(rout[2]), __float_as_int(rout[3])));
-        st_stream_v4(io.index + e0, make_int4(iout[0], iout[1], iout[2], iout[3]));
+        st_stream_v4(io.index + e0, make_int4(idx[0], idx[1], idx[2], idx[3]));
         st_stream_u32(io.terminated + e0, 0u);
         st_stream_u32(io.truncated + e0, trunc_w);
         st_stream_u32(io.unsafe + e0, unsafe_w);
         st_stream_u32(io.count + e0, count_w);
     }
-    if (io.stats) block_flush_stats(ts, s_stats, io.stats);
+    if (io.stats) {
+        const ThreadStats ts = {st_steps, st_unsafe, st_count, st_trunc, st_reward};
+        block_flush_stats(ts, s_stats, io.stats);
+    }
     tick_step_counter(io);
 }
 
@@ -214,35 +234,24 @@ decode_kernel(int64_t n, int64_t ld, int n_cells, uint32_t radix, const uint32_t
     }
 }
 
-template <int C>
-cudaError_t launch_cell_c(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
-{
-    const int64_t n = io.end - io.begin;
-    switch (rng_mode) {
-    case GC_RNG_NONE:
-        cell_step_kernel<C, GC_RNG_NONE><<<grid_for<cell_step_kernel<C, GC_RNG_NONE>>(n, n_sm), kThreads, 0, st>>>(tab, io);
-        break;
-    case GC_RNG_PHILOX:
-        cell_step_kernel<C, GC_RNG_PHILOX><<<grid_for<cell_step_kernel<C, GC_RNG_PHILOX>>(n, n_sm), kThreads, 0, st>>>(tab, io);
-        break;
-    default:
-        cell_step_kernel<C, GC_RNG_REPLAY><<<grid_for<cell_step_kernel<C, GC_RNG_REPLAY>>(n, n_sm), kThreads, 0, st>>>(tab, io);
-        break;
-    }
-    return cudaGetLastError();
-}
-
 }  // namespace
 
 cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
 {
-    switch (tab.n_cells) {
-#define GC_CASE(C) case C: return launch_cell_c<C>(tab, io, rng_mode, n_sm, st);
-        GC_CASE(1) GC_CASE(2) GC_CASE(3) GC_CASE(4) GC_CASE(5) GC_CASE(6) GC_CASE(7) GC_CASE(8)
-        GC_CASE(9) GC_CASE(10) GC_CASE(11) GC_CASE(12) GC_CASE(13) GC_CASE(14) GC_CASE(15) GC_CASE(16)
-#undef GC_CASE
-    default: return cudaErrorInvalidValue;
+    if (tab.n_cells < 1 || tab.n_cells > GC_MAX_CELLS) return cudaErrorInvalidValue;
+    const int64_t n = io.end - io.begin;
+    switch (rng_mode) {
+    case GC_RNG_NONE:
+        cell_step_kernel<GC_RNG_NONE><<<grid_for<cell_step_kernel<GC_RNG_NONE>>(n, n_sm), kThreads, 0, st>>>(tab, io);
+        break;
+    case GC_RNG_PHILOX:
+        cell_step_kernel<GC_RNG_PHILOX><<<grid_for<cell_step_kernel<GC_RNG_PHILOX>>(n, n_sm), kThreads, 0, st>>>(tab, io);
+        break;
+    default:
+        cell_step_kernel<GC_RNG_REPLAY><<<grid_for<cell_step_kernel<GC_RNG_REPLAY>>(n, n_sm), kThreads, 0, st>>>(tab, io);
+        break;
     }
+    return cudaGetLastError();
 }
 
 cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,

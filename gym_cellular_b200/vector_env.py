@@ -68,7 +68,7 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                  difficulty="easy", reward_func=None, stochastic=False, deadlock=False,
                  noise_prob=0.1, dispersal_prob=0.01, env_seed=0, rng_episodic=None,
                  max_episode_steps=None, device=None, env_id_offset=0, emit_side_effects=True,
-                 collect_stats=True, host_chunk_envs=1 << 20, cell_tables=None):
+                 collect_stats=True, host_chunk_envs=1 << 20, cell_tables=None, force_generic_kernel=False):
         self._lib = _lib.load()                      # raises ImportError when the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("CellularVectorEnv needs a CUDA device: there is no CPU fallback")
@@ -125,6 +125,8 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             self.reward_func = reward_func
         if self.rng_episodic:
             flags |= _lib.F_RNG_EPISODIC
+        if force_generic_kernel:
+            flags |= _lib.F_GENERIC_KERNEL
         cfg.flags = flags
         cfg.n_envs, cfg.ld, cfg.env_id_offset = self.num_envs, self.ld, self.env_id_offset
         cfg.seed = self.env_seed & (2 ** 64 - 1)

@@ -68,6 +68,7 @@ typedef enum {
 #define GC_F_RNG_EPISODIC 4u  /* RNG counter = episode step (the reference re-seeds in reset(),
                                  cells3resetVdeadlock.py:131); otherwise the handle's global step  */
 #define GC_F_REWARD_LOG2  16u /* reward = log2(1 + sum) (`nonlinear`, cells3states3actions3.py:47-49) */
+#define GC_F_GENERIC_KERNEL 32u /* always use the generic per-cell kernel, never the pair-table fast path (tests) */
 
 #define GC_MAX_CELLS   16
 #define GC_MAX_LEVELS  8      /* intracellular states / actions per cell */

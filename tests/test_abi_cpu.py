@@ -35,7 +35,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.GcCellTables) == 8 * C.sizeof(C.c_void_p)
     header = open(os.path.join(REPO, "include", "gym_cellular_b200.h")).read()
     for name, val in (("GC_F_NOISE", _lib.F_NOISE), ("GC_F_RNG_EPISODIC", _lib.F_RNG_EPISODIC),
-                      ("GC_F_REWARD_LOG2", _lib.F_REWARD_LOG2), ("GC_MAX_CELLS", _lib.MAX_CELLS),
+                      ("GC_F_REWARD_LOG2", _lib.F_REWARD_LOG2), ("GC_F_GENERIC_KERNEL", _lib.F_GENERIC_KERNEL), ("GC_MAX_CELLS", _lib.MAX_CELLS),
                       ("GC_MAX_LEVELS", _lib.MAX_LEVELS), ("GC_N_STATS", _lib.N_STATS)):
         assert int(re.search(rf"#define {name}\s+(\d+)", header).group(1)) == val
 

@@ -243,6 +243,23 @@ def test_other_shapes(B, O, C, S):
     _rollout(env, ora, 10, np.random.default_rng(C))
 
 
+@pytest.mark.parametrize("C,S,stochastic", [(3, 3, True), (2, 3, False), (16, 4, True), (16, 4, False), (1, 4, True)])
+def test_generic_kernel_equals_oracle(B, O, C, S, stochastic):
+    """The generic per-cell kernel (used for 5-8 levels or per-cell side-effect tables) on shapes the
+    pair-table fast path normally takes: both must agree with the oracle, including side-effect rows."""
+    n = 9001
+    env = B.CellularVectorEnv(num_envs=n, n_cells=C, n_states=S, stochastic=stochastic, env_seed=8, difficulty="hard",
+                              max_episode_steps=6, force_generic_kernel=True)
+    ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, noise=stochastic, seed=8, rng_episodic=True, difficulty="hard",
+                      max_episode_steps=6, reward="nonlinear_rp" if stochastic else "right_polarizing")
+    _rollout(env, ora, 14, np.random.default_rng(C * S), check_every=2)
+    s = env.stats()
+    assert s["env_steps"] == ora.stats[0] and s["unsafe_steps"] == ora.stats[1] and s["episodes_truncated"] == ora.stats[3]
+    obs, rew, *_ = env.step(np.zeros((C, n), np.int8))               # host path through the generic kernel
+    ora.step(np.zeros((C, n), np.int8))
+    assert (np.stack(obs) == ora.state).all()
+
+
 def test_custom_reward_table_and_callable(B, O):
     n = 2048
     tab = np.random.default_rng(0).random((3, 3))
