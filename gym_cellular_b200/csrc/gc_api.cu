@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -134,7 +135,13 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
     cudaError_t e;
     if (env->cfg.kind == GC_KIND_CELLULAR) {
         const int mode = io.replay ? GC_RNG_REPLAY : ((env->cfg.flags & GC_F_NOISE) ? GC_RNG_PHILOX : GC_RNG_NONE);
-        if (env->fast_ok)
+        // Experimental: wide deterministic envs staged tile by tile with TMA bulk copies (gc_cell_tma.cu).
+        // Measured slower than the register-staged kernel (profiles/r01_tuning_log.md), so it is opt-in:
+        // GC_B200_TMA=1 in the environment.
+        static const bool use_tma = [] { const char *v = std::getenv("GC_B200_TMA"); return v && v[0] == '1'; }();
+        if (env->fast_ok && use_tma && mode == GC_RNG_NONE && !io.se_row && env->cfg.n_cells >= 8)
+            e = gc_launch_cell_tma_step(env->tab, io, env->d_pair_lut, env->n_sm, st);
+        else if (env->fast_ok)
             e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, mode, env->n_sm, st);
         else
             e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);

@@ -98,6 +98,9 @@ cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng
 #define GC_PAIR_LUT_ENTRIES (GC_PAIR_LUT_PAIRS + 32)
 cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode,
                                      int n_sm, cudaStream_t stream);
+// TMA bulk-staged variant of the deterministic pair-table step for wide envs (gc_cell_tma.cu)
+cudaError_t gc_launch_cell_tma_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
+                                    cudaStream_t stream);
 cudaError_t gc_launch_cell_rollout(const CellTables &tab, const RolloutIO &io, const uint2 *lut, bool noise,
                                    int n_sm, cudaStream_t stream);
 cudaError_t gc_launch_grid_rollout(const GridParams &gp, const RolloutIO &io, int n_sm, cudaStream_t stream);
