@@ -64,6 +64,10 @@ def launches(path, round_, workload):
            "| kernel | launches | avg us | total us | share |", "|---|---|---|---|---|"]
     for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         out.append(f"| `{k}` | {len(v)} | {sum(v) / len(v):.1f} | {sum(v):.0f} | {100 * sum(v) / total:.1f}% |")
+    out += ["", "Reading: the device-path launches (one kernel of ours per step and sub-batch, `gpu_launches` = steps) are",
+            "the `value` leg; further launches of the same kernels over 1M-env chunks belong to the host path",
+            "(`gc_step_host`, the `e2e` leg) and `*_rollout_kernel` to the fused-rollout side measurement; everything",
+            "`at::` is torch set-up work outside the timed regions."]
     open(os.path.join(OUT, f"{round_}_launches_{workload}.md"), "w").write("\n".join(out) + "\n")
 
 
