@@ -19,7 +19,7 @@ POLICY_RANDOM, POLICY_TABLE = 0, 1
 
 EXPORTS = ["gc_abi_version", "gc_last_error", "gc_create", "gc_destroy", "gc_set_tables",
            "gc_set_global_step", "gc_get_global_step", "gc_sync_global_step", "gc_launch_count", "gc_reset", "gc_step",
-           "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode", "gc_decode"]
+           "gc_bind_step", "gc_step_bound", "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode", "gc_decode"]
 
 
 class GcConfig(C.Structure):
@@ -70,6 +70,8 @@ def load():
     L.gc_launch_count.restype = i64
     L.gc_reset.argtypes = [vp] * 6
     L.gc_step.argtypes = [vp, i64, i64] + [vp] * 13
+    L.gc_bind_step.argtypes = [vp, C.c_int32] + [vp] * 11
+    L.gc_step_bound.argtypes = [vp, C.c_int32, vp]
     L.gc_step_host.argtypes = [vp] * 21 + [i64]
     L.gc_rollout.argtypes = [vp, C.c_int32, C.c_int32] + [vp] * 8
     L.gc_poll_status.argtypes = [vp, vp]

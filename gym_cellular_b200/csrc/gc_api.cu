@@ -77,6 +77,8 @@ struct gc_env {
     uint32_t *d_done;               // block-arrival counter of the step kernels
     uint2 *d_pair_lut;            // fast-path table (GC_PAIR_LUT_ENTRIES), device memory owned by the handle
     bool fast_ok;
+    StepIO bound[GC_MAX_BINDINGS];  // gc_bind_step slots
+    bool bound_set[GC_MAX_BINDINGS];
     cudaStream_t hstream[kHostStreams];
     cudaEvent_t hevent[kHostStreams];
     bool host_ready;
@@ -387,6 +389,33 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
         const uint32_t v = static_cast<uint32_t>(env->global_step);
         GC_CUDA(cudaMemcpyAsync(env->d_step, &v, sizeof(v), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
     }
+    return GC_OK;
+}
+
+int gc_bind_step(gc_env *env, int32_t slot, const int8_t *actions, int8_t *state, int32_t *t, float *reward,
+                 uint32_t *index, uint8_t *terminated, uint8_t *truncated, uint8_t *unsafe, uint8_t *count,
+                 int8_t *se_row, int64_t *stats)
+{
+    if (int rc = check_env(env)) return rc;
+    if (slot < 0 || slot >= GC_MAX_BINDINGS) return fail(GC_ERR_INVALID, "slot must be in [0, %d)", GC_MAX_BINDINGS);
+    if (!actions || !state || !t || !reward || !index || !terminated || !truncated || !unsafe || !count)
+        return fail(GC_ERR_INVALID, "a required device pointer is NULL");
+    env->bound[slot] = make_io(env, 0, env->cfg.n_envs, actions, state, t, reward, index, terminated, truncated,
+                               unsafe, count, se_row, nullptr, stats);
+    env->bound[slot].step_ctr = env->d_step;
+    env->bound[slot].done_ctr = env->d_done;
+    env->bound_set[slot] = true;
+    return GC_OK;
+}
+
+int gc_step_bound(gc_env *env, int32_t slot, void *stream)
+{
+    if (!env || slot < 0 || slot >= GC_MAX_BINDINGS || !env->bound_set[slot])
+        return fail(GC_ERR_INVALID, "gc_step_bound: no binding in this slot");
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    GC_ON_DEVICE(env->cfg.device);
+    if (int rc = launch_step(env, env->bound[slot], static_cast<cudaStream_t>(stream))) return rc;
+    env->global_step += 1;
     return GC_OK;
 }
 

@@ -386,11 +386,24 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         a = self._actions if actions is None else actions
         if a.dtype != torch.int8 or a.shape != (self.n_cells, self.ld) or not a.is_contiguous() or a.device != self.device:
             raise ValueError(f"bind_step needs a contiguous int8 tensor of shape {(self.n_cells, self.ld)} on {self.device}")
-        fn, check, dev = self._lib.gc_step, _lib.check, self.device
+        slot = getattr(self, "_n_bound", 0)
+        check, dev, current_stream = _lib.check, self.device, torch.cuda.current_stream
+        if slot < 16:                      # GC_MAX_BINDINGS: the pointer set lives in the handle
+            self._n_bound = slot + 1
+            check(self._lib.gc_bind_step(self._h, slot, _ptr(a), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
+                                         _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated),
+                                         _ptr(self._unsafe), _ptr(self._count), _ptr(self._se_row), _ptr(self._stats)))
+            fn, h = self._lib.gc_step_bound, self._h
+
+            def launch():
+                rc = fn(h, slot, current_stream(dev).cuda_stream)
+                if rc:
+                    check(rc)
+            return launch
+        fn = self._lib.gc_step
         args = (self._h, 0, self.num_envs, _ptr(a), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
                 _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe),
                 _ptr(self._count), _ptr(self._se_row), None, _ptr(self._stats))
-        current_stream = torch.cuda.current_stream
 
         def launch():
             rc = fn(*args, current_stream(dev).cuda_stream)

@@ -169,6 +169,15 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
             uint8_t *unsafe, uint8_t *count, int8_t *se_row, const double *replay_u, int64_t *stats,
             void *stream);
 
+/* Pre-bound step for tight loops: gc_bind_step stores the pointer set of a full-shard gc_step in one of
+ * GC_MAX_BINDINGS slots of the handle, gc_step_bound launches it (same semantics as gc_step over
+ * [0, n_envs)); the foreign-function call then carries three arguments instead of sixteen. */
+#define GC_MAX_BINDINGS 16
+int gc_bind_step(gc_env *env, int32_t slot, const int8_t *actions, int8_t *state, int32_t *t, float *reward,
+                 uint32_t *index, uint8_t *terminated, uint8_t *truncated, uint8_t *unsafe, uint8_t *count,
+                 int8_t *se_row, int64_t *stats);
+int gc_step_bound(gc_env *env, int32_t slot, void *stream);
+
 /* The same step for a HOST caller: h_* are host buffers (pinned for full speed) in the same
  * layouts with row stride ld; d_* the caller-owned resident device arrays.  Copies the actions in,
  * steps, copies state/reward/index/flags out, pipelined over chunks on the handle's own streams;
