@@ -27,6 +27,20 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
 {
     __shared__ uint32_t s_lut[GC_GRID_LUT_ENTRIES];
     __shared__ unsigned long long s_stats[5];
+    const int64_t ld = io.ld;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
+    // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
+    // reads 32 bytes per word, so without the prefetch too few bytes are in flight per SM to cover the
+    // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).  The first word's inputs are
+    // requested before the table is staged, so that the two latencies overlap.
+    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x) * kEPT;
+    uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;
+    int4 p_t = make_int4(0, 0, 0, 0);
+    if (e0 < io.end) {
+        p_s0 = ld_stream_u32(io.state + e0); p_s1 = ld_stream_u32(io.state + ld + e0);
+        p_a0 = ld_stream_u32(io.actions + e0); p_a1 = ld_stream_u32(io.actions + ld + e0);
+        p_t = ld_stream_v4(io.t + e0);
+    }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
@@ -37,19 +51,6 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
 
     const uint32_t step_counter = launch_step_counter(io);
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
-    const int64_t ld = io.ld;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
-    // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
-    // reads 32 bytes per word, so without the prefetch too few bytes are in flight per SM to cover the
-    // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).
-    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x) * kEPT;
-    uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;
-    int4 p_t = make_int4(0, 0, 0, 0);
-    if (e0 < io.end) {
-        p_s0 = ld_stream_u32(io.state + e0); p_s1 = ld_stream_u32(io.state + ld + e0);
-        p_a0 = ld_stream_u32(io.actions + e0); p_a1 = ld_stream_u32(io.actions + ld + e0);
-        p_t = ld_stream_v4(io.t + e0);
-    }
     for (; e0 < io.end; e0 += stride) {
         const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
