@@ -132,24 +132,32 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
                 }
             }
         }
-        uint32_t trunc_w = 0, count_w = 0, se0w = 0, se1w = 0, rew_w = 0;
-        int tout[kEPT];
+        // Everything below works on the four envs at once (byte lanes).  misc byte of an entry:
+        // bits 0-1 reward, 2-3 barren jurisdictions, 4 / 5 side effects [0][0] / [0][1] 'safe', 6 bad action.
+        const uint32_t m01 = prmt(ent[0], ent[1], 0x0062), m23 = prmt(ent[2], ent[3], 0x0062);
+        const uint32_t miscw = prmt(m01, m23, 0x5410);
+        const uint32_t vbytes = valid_bytes(rem);
+        bad_bits |= miscw & vbytes;
+        const uint32_t rew_w = miscw & 0x03030303u, count_w = (miscw >> 2) & 0x03030303u;
+        const uint32_t se0w = (miscw >> 4) & 0x01010101u, se1w = (miscw >> 5) & 0x01010101u;
+        const uint32_t u = prmt(ent[0], ent[1], 0x5140), v = prmt(ent[2], ent[3], 0x5140);
+        uint32_t row0 = prmt(u, v, 0x5410), row1 = prmt(u, v, 0x7632);         // next codes, byte 0 / byte 1
+        uint32_t trunc_w = 0;
+        int tout[kEPT] = {tin[0] + 1, tin[1] + 1, tin[2] + 1, tin[3] + 1};
+        if (io.max_episode_steps > 0) {
+            uint32_t keep = 0xFFFFFFFFu;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                if (tout[e] >= io.max_episode_steps) { tout[e] = 0; trunc_w |= 1u << (8 * e); keep &= ~(0xFFu << (8 * e)); }
+            row0 = (row0 & keep) | (0x0F0F0F0Fu & ~keep);                       // reset codes 15 / 18: grid_world.py:238-259
+            row1 = (row1 & keep) | (0x12121212u & ~keep);
+        }
         float rout[kEPT];
         uint32_t iout[kEPT];
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
-            const uint32_t rew = (ent[e] >> 16) & 3u, nb = (ent[e] >> 18) & 3u;
-            int tn = tin[e] + 1;
-            uint32_t tr = 0;
-            if (e < rem) bad_bits |= ent[e];
-            if (io.max_episode_steps > 0 && tn >= io.max_episode_steps) {
-                tr = 1; tn = 0;
-                ent[e] = (ent[e] & 0xFFFF0000u) | 15u | (18u << 8);               // grid_world.py:238-259
-            }
-            tout[e] = tn; rout[e] = static_cast<float>(rew);
-            iout[e] = (ent[e] & 0xFFu) + 20u * ((ent[e] >> 8) & 0xFFu);
-            trunc_w |= tr << (8 * e); count_w |= nb << (8 * e); rew_w |= rew << (8 * e);
-            se0w |= ((ent[e] >> 20) & 1u) << (8 * e); se1w |= ((ent[e] >> 21) & 1u) << (8 * e);
+            rout[e] = static_cast<float>(byte_of(rew_w, e));
+            iout[e] = byte_of(row0, e) + 20u * byte_of(row1, e);
         }
         {
             const uint32_t vb = valid_bytes(rem);
@@ -158,10 +166,8 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             st_trunc = add_bytes(trunc_w & vb, st_trunc);
             st_reward = add_bytes(rew_w & vb, st_reward);
         }
-        // SoA rows of the next state: byte 0 / byte 1 of the four entries
-        const uint32_t u = prmt(ent[0], ent[1], 0x5140), v = prmt(ent[2], ent[3], 0x5140);
-        st_stream_u32(io.state + e0, prmt(u, v, 0x5410));
-        st_stream_u32(io.state + ld + e0, prmt(u, v, 0x7632));
+        st_stream_u32(io.state + e0, row0);
+        st_stream_u32(io.state + ld + e0, row1);
         if (io.se_row) {
             st_stream_u32(io.se_row + e0, se0w);
             st_stream_u32(io.se_row + ld + e0, se1w);
@@ -175,7 +181,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         st_stream_u32(io.unsafe + e0, 0u);                          // never 'unsafe': grid_world.py:174-175
         st_stream_u32(io.count + e0, count_w);
     }
-    if (bad_bits & (1u << 22)) atomicOr(io.status, 1ull);
+    if (bad_bits & 0x40404040u) atomicOr(io.status, 1ull);
     if (io.stats) {
         const ThreadStats ts = {st_steps, 0, st_count, st_trunc, static_cast<long long>(st_reward) << 24};
         block_flush_stats(ts, s_stats, io.stats);
