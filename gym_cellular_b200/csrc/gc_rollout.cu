@@ -55,7 +55,7 @@ cell_rollout_kernel(const __grid_constant__ CellTables tab, const __grid_constan
     __shared__ uint2 s_single[N_SINGLE];
     __shared__ unsigned long long s_stats[5];
     const uint32_t step0 = io.step_ctr ? *reinterpret_cast<const volatile uint32_t *>(io.step_ctr) : 0u;
-    for (int i = threadIdx.x; i < N_PAIR; i += kThreads) s_pair[i] = lut[i];
+    for (int i = threadIdx.x; i < N_PAIR; i += blockDim.x) s_pair[i] = lut[i];
     if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
@@ -64,8 +64,8 @@ cell_rollout_kernel(const __grid_constant__ CellTables tab, const __grid_constan
     long long st_reward = 0;
     const int64_t ld = io.ld;
     const uint32_t A = static_cast<uint32_t>(tab.n_actions);
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
-    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT; e0 < io.n; e0 += stride) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * kEPT;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * kEPT; e0 < io.n; e0 += stride) {
         const int rem = static_cast<int>(io.n - e0 < kEPT ? io.n - e0 : kEPT);
         const uint32_t vb = valid_bytes(rem);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
@@ -221,15 +221,15 @@ grid_rollout_kernel(const __grid_constant__ GridParams gp, const __grid_constant
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (int i = threadIdx.x; i < GC_GRID_LUT_ENTRIES / 4; i += kThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < GC_GRID_LUT_ENTRIES / 4; i += blockDim.x) dst[i] = src[i];
     }
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     const int64_t ld = io.ld;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
-    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT; e0 < io.n; e0 += stride) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * kEPT;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * kEPT; e0 < io.n; e0 += stride) {
         const int rem = static_cast<int>(io.n - e0 < kEPT ? io.n - e0 : kEPT);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
         const uint32_t grp_lo = static_cast<uint32_t>(gid0 >> 2), grp_hi = static_cast<uint32_t>(gid0 >> 34);
@@ -320,13 +320,26 @@ grid_rollout_kernel(const __grid_constant__ GridParams gp, const __grid_constant
     tick_step_counter(io.step_ctr, io.done_ctr, static_cast<uint32_t>(io.n_steps));
 }
 
+// A rollout is compute-bound, so a small batch should occupy every SM: when the batch does not fill the
+// GPU with 256-thread blocks, 64-thread blocks are launched instead (the kernels size themselves by
+// blockDim.x).
+inline int rollout_threads(int64_t n, int n_sm) { return (n + kEPT - 1) / kEPT < static_cast<int64_t>(n_sm) * kThreads * 2 ? 64 : kThreads; }
+
+inline int rollout_grid(int64_t n, int threads, int n_sm, int blocks_per_sm_256)
+{
+    const int64_t need = (n + threads * kEPT - 1) / (threads * kEPT);
+    const int64_t cap = static_cast<int64_t>(n_sm) * blocks_per_sm_256 * (kThreads / threads);
+    return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
 template <int C>
 cudaError_t launch_rollout_c(const CellTables &tab, const RolloutIO &io, const uint2 *lut, bool noise, int n_sm, cudaStream_t st)
 {
+    const int threads = rollout_threads(io.n, n_sm), grid = rollout_grid(io.n, threads, n_sm, 2);
     if (noise)
-        cell_rollout_kernel<C, true><<<grid_for<cell_rollout_kernel<C, true>>(io.n, n_sm), kThreads, 0, st>>>(tab, io, lut);
+        cell_rollout_kernel<C, true><<<grid, threads, 0, st>>>(tab, io, lut);
     else
-        cell_rollout_kernel<C, false><<<grid_for<cell_rollout_kernel<C, false>>(io.n, n_sm), kThreads, 0, st>>>(tab, io, lut);
+        cell_rollout_kernel<C, false><<<grid, threads, 0, st>>>(tab, io, lut);
     return cudaGetLastError();
 }
 
@@ -346,6 +359,8 @@ cudaError_t gc_launch_cell_rollout(const CellTables &tab, const RolloutIO &io, c
 
 cudaError_t gc_launch_grid_rollout(const GridParams &gp, const RolloutIO &io, int n_sm, cudaStream_t st)
 {
-    grid_rollout_kernel<<<grid_for<grid_rollout_kernel>(io.n, n_sm), kThreads, 0, st>>>(gp, io);
+    // the 40 KB table is staged per block: keep 256-thread blocks unless the batch is really small
+    const int threads = (io.n + kEPT - 1) / kEPT < static_cast<int64_t>(n_sm) * kThreads / 2 ? 64 : kThreads;
+    grid_rollout_kernel<<<rollout_grid(io.n, threads, n_sm, 4), threads, 0, st>>>(gp, io);
     return cudaGetLastError();
 }
