@@ -20,12 +20,15 @@ namespace {
 #define GC_GRID_MINB 1
 #endif
 constexpr int kGridThreads = GC_GRID_THREADS;
+// largest index the masked inputs can form: (31 + 20 * 31) * 25 + 7 + 5 * 7, rounded up
+constexpr int kGridLutAlloc = ((31 + 20 * 31) * 25 + 42 + 1 + 3) / 4 * 4;
+constexpr int kGridSmemBytes = kGridLutAlloc * 4;
 
 template <int RNG>
 __global__ void __launch_bounds__(kGridThreads, GC_GRID_MINB)
 grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ StepIO io)
 {
-    __shared__ uint32_t s_lut[GC_GRID_LUT_ENTRIES];
+    extern __shared__ __align__(16) uint32_t s_lut[];          // kGridLutAlloc entries, the first 10,000 staged
     __shared__ unsigned long long s_stats[5];
     const int64_t ld = io.ld;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
@@ -64,17 +67,16 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             p_t = ld_stream_v4(io.t + en);
         }
         const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
-        // action codes above 4 mean "no position" like 4 (per-byte min(a, 4)); state codes are ours
-        a0w = __vminu4(a0w, 0x04040404u);
-        a1w = __vminu4(a1w, 0x04040404u);
-        const uint32_t actw = a0w + a1w * 5u;                       // a_0 + 5 a_1 <= 24 per byte
+        // Table index (code_0 + 20 code_1) * 25 + a_0 + 5 a_1 of the envs (0, 2) and (1, 3) in the two 16-bit
+        // lanes of a word.  Codes are masked to 5 bits and actions to 3 bits, which bounds the index by
+        // kGridLutAlloc: out-of-range inputs (never produced by the kernels) read padding, not foreign memory.
+        const uint32_t s0m = s0w & 0x1F1F1F1Fu, s1m = s1w & 0x1F1F1F1Fu;
+        const uint32_t actw = (a0w & 0x07070707u) + (a1w & 0x07070707u) * 5u;
+        const uint32_t i02 = ((s0m & 0x00FF00FFu) + 20u * (s1m & 0x00FF00FFu)) * 25u + (actw & 0x00FF00FFu);
+        const uint32_t i13 = (((s0m >> 8) & 0x00FF00FFu) + 20u * ((s1m >> 8) & 0x00FF00FFu)) * 25u + ((actw >> 8) & 0x00FF00FFu);
         uint32_t ent[kEPT];
-#pragma unroll
-        for (int e = 0; e < kEPT; ++e) {
-            const uint32_t tab = byte_of(s0w, e) + 20u * byte_of(s1w, e);
-            const uint32_t ix = tab * 25u + byte_of(actw, e);
-            ent[e] = s_lut[ix < GC_GRID_LUT_ENTRIES ? ix : 0];
-        }
+        ent[0] = s_lut[i02 & 0xFFFFu]; ent[1] = s_lut[i13 & 0xFFFFu];
+        ent[2] = s_lut[i02 >> 16]; ent[3] = s_lut[i13 >> 16];
         // Seed dispersal (grid_world.py:160-162): unless both jurisdictions were barren, one uniform
         // draw; below dispersal_prob the 2x2 bits and the jurisdiction index are drawn as well.  The
         // trigger words of the four envs of a thread are the four words of ONE Philox block (keyed by
@@ -153,12 +155,11 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             row1 = (row1 & keep) | (0x12121212u & ~keep);
         }
         float rout[kEPT];
-        uint32_t iout[kEPT];
 #pragma unroll
-        for (int e = 0; e < kEPT; ++e) {
-            rout[e] = static_cast<float>(byte_of(rew_w, e));
-            iout[e] = byte_of(row0, e) + 20u * byte_of(row1, e);
-        }
+        for (int e = 0; e < kEPT; ++e) rout[e] = static_cast<float>(byte_of(rew_w, e));
+        const uint32_t x02 = (row0 & 0x00FF00FFu) + 20u * (row1 & 0x00FF00FFu);             // code_0 + 20 code_1
+        const uint32_t x13 = ((row0 >> 8) & 0x00FF00FFu) + 20u * ((row1 >> 8) & 0x00FF00FFu);
+        const uint32_t iout[kEPT] = {x02 & 0xFFFFu, x13 & 0xFFFFu, x02 >> 16, x13 >> 16};
         {
             const uint32_t vb = valid_bytes(rem);
             st_steps += rem;
@@ -191,12 +192,33 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
 
 }  // namespace
 
+template <auto Kernel>
+int grid_blocks(int64_t n, int n_sm, cudaError_t *err)
+{
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        *err = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGridSmemBytes);
+        if (*err != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kGridThreads, kGridSmemBytes) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+    }
+    const int64_t need = (n + kGridThreads * kEPT - 1) / (kGridThreads * kEPT);
+    const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;
+    return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
 cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
 {
     const int64_t n = io.end - io.begin;
-    if (rng_mode == GC_RNG_REPLAY)
-        grid_step_kernel<GC_RNG_REPLAY><<<grid_for<grid_step_kernel<GC_RNG_REPLAY>, kGridThreads>(n, n_sm), kGridThreads, 0, st>>>(gp, io);
-    else
-        grid_step_kernel<GC_RNG_PHILOX><<<grid_for<grid_step_kernel<GC_RNG_PHILOX>, kGridThreads>(n, n_sm), kGridThreads, 0, st>>>(gp, io);
+    cudaError_t err = cudaSuccess;
+    if (rng_mode == GC_RNG_REPLAY) {
+        const int g = grid_blocks<grid_step_kernel<GC_RNG_REPLAY>>(n, n_sm, &err);
+        if (err != cudaSuccess) return err;
+        grid_step_kernel<GC_RNG_REPLAY><<<g, kGridThreads, kGridSmemBytes, st>>>(gp, io);
+    } else {
+        const int g = grid_blocks<grid_step_kernel<GC_RNG_PHILOX>>(n, n_sm, &err);
+        if (err != cudaSuccess) return err;
+        grid_step_kernel<GC_RNG_PHILOX><<<g, kGridThreads, kGridSmemBytes, st>>>(gp, io);
+    }
     return cudaGetLastError();
 }

@@ -147,7 +147,8 @@ int gc_reset(gc_env *env, const uint8_t *mask, int8_t *state, int32_t *t, uint32
 /* One env.step() for envs [env_begin, env_begin + env_count) of the shard (pass 0, n_envs for all;
  * env_begin % 16 == 0).  All pointers are device pointers to the FULL arrays.
  *   actions    int8  [C][ld]  in      cellular: level chosen per cell; grid world: go-to position
- *                                     code per jurisdiction, 0..3 = row*2+col, 4 = none
+ *                                     code per jurisdiction, 0..3 = row*2+col, 4 = none (other codes are
+ *                                     invalid: the kernels stay memory-safe, the result is unspecified)
  *   state      int8  [C][ld]  in/out  cellular: level per cell; grid world: the reference's own
  *                                     cellular code per jurisdiction (grid_world.py:349-359)
  *   t          int32 [ld]     in/out  episode step (data['time_step'])
