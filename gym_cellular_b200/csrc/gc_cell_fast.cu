@@ -242,7 +242,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
             const uint32_t uns = ((acc.first[e] >> 12) & 1u) | ((((acc.orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
             const uint32_t cnt = acc.add[e] & 31u;
             float rr = acc.r[e];
-            if (tab.reward_log2) rr = log1pf(rr) * 1.44269504088896341f;
+            if (tab.reward_log2) rr = log2_1p(rr);
             rout[e] = rr;
             unsafe_w |= uns << (8 * e); count_w |= cnt << (8 * e);
             if (e < rem) st_reward += __float2int_rn(rr * 16777216.0f);          // |reward| < 128

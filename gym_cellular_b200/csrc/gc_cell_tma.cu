@@ -207,7 +207,7 @@ cell_tma_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ 
                 const uint32_t rowmask = (tab.unsafe_rows >> (8 * s0n)) & 0xFFu;
                 const uint32_t uns = ((first[e] >> 12) & 1u) | ((((orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
                 float rr = r[e];
-                if (tab.reward_log2) rr = log1pf(rr) * 1.44269504088896341f;
+                if (tab.reward_log2) rr = log2_1p(rr);
                 rout[e] = rr;
                 unsafe_w |= uns << (8 * e); count_w |= (add[e] & 31u) << (8 * e);
                 if (e < rem) st_reward += __float2int_rn(rr * 16777216.0f);

@@ -133,7 +133,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
             float rr = r[e];
-            if (tab.reward_log2) rr = log1pf(rr) * 1.44269504088896341f;
+            if (tab.reward_log2) rr = log2_1p(rr);
             rout[e] = rr;
             if (e < rem) st_reward += __float2int_rn(rr * 16777216.0f);
         }

@@ -177,7 +177,7 @@ cell_rollout_kernel(const __grid_constant__ CellTables tab, const __grid_constan
                 const uint32_t rowmask = (tab.unsafe_rows >> (8 * s0n)) & 0xFFu;
                 const uint32_t uns = ((first[e] >> 12) & 1u) | ((((orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
                 float rr = r[e];
-                if (tab.reward_log2) rr = log1pf(rr) * 1.44269504088896341f;
+                if (tab.reward_log2) rr = log2_1p(rr);
                 ret[e] += rr;
                 nuns[e] += uns;
                 unsafe_w |= uns << (8 * e); count_w |= (add[e] & 31u) << (8 * e);
