@@ -56,20 +56,28 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
                                          const int (&tin)[kEPT], uint32_t keep, const uint32_t (&sw)[4],
                                          const uint32_t (&aw)[4], EnvAcc &acc)
 {
-    uint32_t rnd[kEPT][4];
+    // fb[e]: bit i = the noise draw of cell (c0 + i) of env e fired (the table ignores the bit where the
+    // (level, action) pair consumes no draw).  The four random words are reduced to four bits at once so
+    // that only one register per env stays live.
+    uint32_t fb[kEPT] = {0, 0, 0, 0};
     if (RNG == GC_RNG_PHILOX) {
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
+            uint32_t w[4];
             const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
-            philox4x32_10(gid_lo | e, gid_hi, ctr, static_cast<uint32_t>(c0 >> 2), io.round_key, rnd[e]);
+            philox4x32_10(gid_lo | e, gid_hi, ctr, static_cast<uint32_t>(c0 >> 2), io.round_key, w);
+            const uint32_t thr = tab.noise_thr_m1;
+            fb[e] = (w[0] <= thr ? 1u : 0u) | (w[1] <= thr ? 2u : 0u) | (w[2] <= thr ? 4u : 0u) | (w[3] <= thr ? 8u : 0u);
+            if (!tab.noise_thr_nz) fb[e] = 0;
         }
+    } else if (RNG == GC_RNG_REPLAY) {
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e)
+            if (e < rem)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    fb[e] |= (io.replay[(e0 + e) * C + c0 + i] < tab.noise_prob ? 1u : 0u) << i;
     }
-    // did the noise draw of cell (c0 + i) fire for env e?  (the table ignores it where no draw is consumed)
-    auto fire = [&](int e, int i) -> uint32_t {
-        if (RNG == GC_RNG_PHILOX) return (tab.noise_thr_nz && rnd[e][i] <= tab.noise_thr_m1) ? 1u : 0u;
-        if (RNG == GC_RNG_REPLAY) return (e < rem && io.replay[(e0 + e) * C + c0 + i] < tab.noise_prob) ? 1u : 0u;
-        return 0u;
-    };
     const int64_t ld = io.ld;
     uint32_t q = 0;                       // index digits of the group folded into one byte per env
     uint32_t rows[4];
@@ -83,7 +91,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) {
                 uint32_t ix = byte_of(pidx, e);
-                if (RNG != GC_RNG_NONE) ix |= (fire(e, i) << 8) | (fire(e, i + 1) << 9);
+                if (RNG != GC_RNG_NONE) ix |= ((fb[e] >> i) & 3u) << 8;
                 const uint2 ent = s_pair[ix];
                 acc.r[e] += __uint_as_float(ent.y);
                 inf[e] = ent.x;
@@ -93,7 +101,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) {
                 uint32_t ix = byte_of(sidx, e) & 15u;
-                if (RNG != GC_RNG_NONE) ix |= fire(e, i) << 4;
+                if (RNG != GC_RNG_NONE) ix |= ((fb[e] >> i) & 1u) << 4;
                 const uint2 ent = s_single[ix];
                 acc.r[e] += __uint_as_float(ent.y);
                 inf[e] = ent.x;
