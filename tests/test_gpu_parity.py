@@ -767,3 +767,19 @@ def test_tma_variant(B):
         assert r.returncode == 0, r.stderr[-600:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1] and outs[0].startswith("crc")
+
+
+def test_example_plan_and_rollout(B):
+    """examples/plan_and_rollout.py: value iteration on the exported model beats random play."""
+    import importlib.util
+    from conftest import REPO
+    spec = importlib.util.spec_from_file_location("plan_and_rollout", REPO + "/examples/plan_and_rollout.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import sys
+    argv, sys.argv = sys.argv, ["x", "--env", "polarisation", "--envs", "65536", "--steps", "64"]
+    try:
+        res = mod.main()
+    finally:
+        sys.argv = argv
+    assert res["planned"][0] > res["random"][0] * 1.5
