@@ -167,10 +167,26 @@ def launch_step(batch, i):
 
 
 def time_device_path(batches, steps, warmup, dist, device, sampler_index):
+    """Device path.  Independent sub-batches (the mixed config 5) step on one stream each, so that
+    the tail of one kernel overlaps the head of the other; everything is bracketed by events on the
+    main stream, which the side streams are ordered against."""
     import torch
-    for i in range(warmup):
-        for b in batches:
-            launch_step(b, i)
+    main = torch.cuda.current_stream(device)
+    streams = [main] if len(batches) == 1 else [torch.cuda.Stream(device=device) for _ in batches]
+
+    def run(lo, hi):
+        for s in streams:
+            if s is not main:
+                s.wait_stream(main)
+        for i in range(lo, hi):
+            for b, s in zip(batches, streams):
+                with torch.cuda.stream(s):
+                    launch_step(b, i)
+        for s in streams:
+            if s is not main:
+                main.wait_stream(s)
+
+    run(0, warmup)
     torch.cuda.synchronize(device)
     if dist is not None:
         dist.barrier()
@@ -178,11 +194,9 @@ def time_device_path(batches, steps, warmup, dist, device, sampler_index):
     launches0 = sum(b["env"].launch_count for b in batches)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(sampler_index) as clk:
-        start.record()
-        for i in range(steps):
-            for b in batches:
-                launch_step(b, warmup + i)
-        stop.record()
+        start.record(main)
+        run(warmup, warmup + steps)
+        stop.record(main)
         stop.synchronize()
     ms = start.elapsed_time(stop)
     launches = sum(b["env"].launch_count for b in batches) - launches0
