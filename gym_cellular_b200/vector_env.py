@@ -364,6 +364,16 @@ class CellularVectorEnv(gym.vector.VectorEnv):
     def step_device(self, actions=None, replay_u=None):
         """Launch one step on the current stream; no host synchronisation, no output marshalling.
         `actions`: None = the env's own action buffer (`action_buffer`) already holds them."""
+        if replay_u is None and type(actions) is torch.Tensor:
+            # hot path: the same action tensor(s) again and again -> a pre-bound launch per buffer
+            cache = self.__dict__.setdefault("_bound_cache", {})
+            call = cache.get(actions.data_ptr())
+            if call is None and len(cache) < 8 and actions.shape == (self.n_cells, self.ld) \
+                    and actions.dtype == torch.int8 and actions.is_contiguous() and actions.device == self.device:
+                call = cache[actions.data_ptr()] = (self.bind_step(actions), actions)   # keeps the buffer alive
+            if call is not None and call[1] is actions:
+                call[0]()
+                return
         a_ptr = _ptr(self._actions)
         if actions is not None:
             a_ptr = self._load_actions_device(actions)
