@@ -136,7 +136,9 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
     if (io.end <= io.begin) return GC_OK;
     cudaError_t e;
     if (env->cfg.kind == GC_KIND_CELLULAR) {
-        const int mode = io.replay ? GC_RNG_REPLAY : ((env->cfg.flags & GC_F_NOISE) ? GC_RNG_PHILOX : GC_RNG_NONE);
+        // noise with probability 0 never fires: the deterministic kernels then do the same job
+        const bool draws = (env->cfg.flags & GC_F_NOISE) && env->tab.noise_thr_nz;
+        const int mode = io.replay ? GC_RNG_REPLAY : (draws ? GC_RNG_PHILOX : GC_RNG_NONE);
         // Experimental: wide deterministic envs staged tile by tile with TMA bulk copies (gc_cell_tma.cu).
         // Measured slower than the register-staged kernel (profiles/r01_tuning_log.md), so it is opt-in:
         // GC_B200_TMA=1 in the environment.

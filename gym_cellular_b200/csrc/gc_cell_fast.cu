@@ -66,9 +66,8 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
             uint32_t w[4];
             const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
             philox4x32_10(gid_lo | e, gid_hi, ctr, static_cast<uint32_t>(c0 >> 2), io.round_key, w);
-            const uint32_t thr = tab.noise_thr_m1;
+            const uint32_t thr = tab.noise_thr_m1;            // threshold - 1; a zero threshold never gets here (gc_api.cu)
             fb[e] = (w[0] <= thr ? 1u : 0u) | (w[1] <= thr ? 2u : 0u) | (w[2] <= thr ? 4u : 0u) | (w[3] <= thr ? 8u : 0u);
-            if (!tab.noise_thr_nz) fb[e] = 0;
         }
     } else if (RNG == GC_RNG_REPLAY) {
 #pragma unroll
@@ -243,17 +242,15 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
 
         uint32_t unsafe_w = 0, count_w = 0;
         float rout[kEPT];
+        log2_1p_x4(tab.reward_log2, acc.r, rout);
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
             const uint32_t s0n = (acc.first[e] >> 16) & 3u;
             const uint32_t rowmask = (tab.unsafe_rows >> (8 * s0n)) & 0xFFu;
             const uint32_t uns = ((acc.first[e] >> 12) & 1u) | ((((acc.orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
             const uint32_t cnt = acc.add[e] & 31u;
-            float rr = acc.r[e];
-            if (tab.reward_log2) rr = log2_1p(rr);
-            rout[e] = rr;
             unsafe_w |= uns << (8 * e); count_w |= cnt << (8 * e);
-            if (e < rem) st_reward += __float2int_rn(rr * 16777216.0f);          // |reward| < 128
+            if (e < rem) st_reward += __float2int_rn(rout[e] * 16777216.0f);     // |reward| < 128
         }
         {
             const uint32_t vb = valid_bytes(rem);

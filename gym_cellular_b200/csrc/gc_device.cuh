@@ -53,7 +53,7 @@ __device__ __forceinline__ void st_stream_v4(void *p, int4 v) { __stcs(reinterpr
 // Per-thread statistics, reduced once per block at kernel exit: warp shuffles, one shared-memory
 // atomic per warp, one global atomic per block and statistic.
 struct ThreadStats {
-    unsigned long long steps, unsafe, count, truncated;
+    uint32_t steps, unsafe, count, truncated;     // per thread and launch: < 2^32
     long long reward_q24;
 };
 
@@ -87,22 +87,48 @@ __device__ __forceinline__ void tick_step_counter(const uint32_t *step_ctr, uint
 __device__ __forceinline__ void tick_step_counter(const StepIO &io) { tick_step_counter(io.step_ctr, io.done_ctr, 1u); }
 
 // log2(1 + r) of the `nonlinear` rewards (np.log2(1 + .), cells3states3actions3.py:47-49) to ~4e-7
-// relative: for r <= 1 (always, for the reference's 2- and 3-cell envs) 2 atanh(s) / ln 2 with s = r / (2 + r)
-// <= 1/3 as a degree-6 polynomial in s^2 (11 instructions instead of the ~25 of log1pf); log1pf beyond.
+// relative: for -1/2 <= r <= 1 (always, for the reference's 2- and 3-cell envs) 2 atanh(s) / ln 2 with
+// s = r / (2 + r), |s| <= 1/3, as a degree-6 polynomial in s^2 with 2 / ln 2 folded into the
+// coefficients (10 FMA-pipe instructions and one MUFU.RCP instead of the ~25 of log1pf); log1pf beyond.
+__device__ __forceinline__ float log2_1p_small(float r)
+{
+    float s;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(s) : "f"(r), "f"(2.0f + r));
+    const float z = s * s;
+    constexpr float k = 2.88539008177792681f;                // 2 / ln 2
+    float p = k / 13.0f;
+    p = fmaf(p, z, k / 11.0f);
+    p = fmaf(p, z, k / 9.0f);
+    p = fmaf(p, z, k / 7.0f);
+    p = fmaf(p, z, k / 5.0f);
+    p = fmaf(p, z, k / 3.0f);
+    p = fmaf(p, z, k);
+    return s * p;
+}
+
 __device__ __forceinline__ float log2_1p(float r)
 {
-    if (r <= 1.0f) {
-        const float s = __fdividef(r, 2.0f + r), z = s * s;
-        float p = 1.0f / 13.0f;
-        p = fmaf(p, z, 1.0f / 11.0f);
-        p = fmaf(p, z, 1.0f / 9.0f);
-        p = fmaf(p, z, 1.0f / 7.0f);
-        p = fmaf(p, z, 1.0f / 5.0f);
-        p = fmaf(p, z, 1.0f / 3.0f);
-        p = fmaf(p, z, 1.0f);
-        return s * p * 2.88539008177792681f;               // 2 / ln 2
-    }
+    if (r >= -0.5f && r <= 1.0f) return log2_1p_small(r);
     return log1pf(r) * 1.44269504088896341f;
+}
+
+// The same for the four envs of a thread: one range test (two FMNMX trees) guards the polynomial path
+// of all four, so the common case carries no per-env branch.
+__device__ __forceinline__ void log2_1p_x4(int enabled, const float (&r)[4], float (&out)[4])
+{
+    if (!enabled) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = r[e];
+        return;
+    }
+    const float hi = fmaxf(fmaxf(r[0], r[1]), fmaxf(r[2], r[3])), lo = fminf(fminf(r[0], r[1]), fminf(r[2], r[3]));
+    if (lo >= -0.5f && hi <= 1.0f) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = log2_1p_small(r[e]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = log1pf(r[e]) * 1.44269504088896341f;
+    }
 }
 
 // byte mask of the envs of a 4-env word that lie inside the launch range (rem = envs left, >= 1)
@@ -111,23 +137,36 @@ __device__ __forceinline__ uint32_t valid_bytes(int rem) { return rem >= 4 ? 0xF
 // sum of the four bytes of w added to acc (one IDP.4A)
 __device__ __forceinline__ uint32_t add_bytes(uint32_t w, uint32_t acc) { return __dp4a(w, 0x01010101u, acc); }
 
+// Sum of a 64-bit value over the warp with three REDUX.SUM instead of ten shuffles: the two 16-bit
+// halves of the low word cannot overflow 32 bits over 32 lanes, and the high words add modulo 2^32,
+// which is what their place in a 64-bit sum (modulo 2^64, signed or not) requires.
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+    const uint32_t a = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu);
+    const uint32_t b = __reduce_add_sync(0xffffffffu, lo >> 16);
+    const uint32_t c = __reduce_add_sync(0xffffffffu, hi);
+    return static_cast<unsigned long long>(a) + (static_cast<unsigned long long>(b) << 16) +
+           (static_cast<unsigned long long>(c) << 32);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(uint32_t v)
+{
+    const uint32_t a = __reduce_add_sync(0xffffffffu, v & 0xFFFFu);
+    const uint32_t b = __reduce_add_sync(0xffffffffu, v >> 16);
+    return static_cast<unsigned long long>(a) + (static_cast<unsigned long long>(b) << 16);
 }
 
 __device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigned long long *s_stats,
                                                   unsigned long long *g_stats)
 {
     // s_stats zeroed before the main loop (with a __syncthreads in between)
-    unsigned long long v[5] = {ts.steps, ts.unsafe, ts.count, ts.truncated,
-                               static_cast<unsigned long long>(ts.reward_q24)};
+    const unsigned long long w[5] = {warp_sum(ts.steps), warp_sum(ts.unsafe), warp_sum(ts.count), warp_sum(ts.truncated),
+                                     warp_sum(static_cast<unsigned long long>(ts.reward_q24))};
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const unsigned long long w = warp_sum(v[i]);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_stats[i], w);
+        for (int i = 0; i < 5; ++i)
+            if (w[i]) atomicAdd(&s_stats[i], w[i]);
     }
     __syncthreads();
     if (threadIdx.x < 5 && s_stats[threadIdx.x]) atomicAdd(&g_stats[threadIdx.x], s_stats[threadIdx.x]);
