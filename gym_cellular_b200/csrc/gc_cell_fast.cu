@@ -44,6 +44,7 @@ struct EnvAcc {
     uint32_t orr[kEPT];     // OR of info words of the cells j >= 2: bits 8-11 = levels present
     uint32_t first[kEPT];   // info word of the pair (cell 0, cell 1) (or of cell 0 alone when C == 1)
     uint32_t idx[kEPT];     // tabular index
+    uint32_t s0w;           // next level of cell 0 (before an auto-reset), byte lane e = env e
 };
 
 // One group of N <= 4 consecutive cells starting at cell c0 (c0 % 4 == 0) for the 4 envs of a thread.
@@ -92,7 +93,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
                 uint32_t ix = byte_of(pidx, e);
                 if (RNG != GC_RNG_NONE) ix |= ((fb[e] >> i) & 3u) << 8;
                 const uint2 ent = s_pair[ix];
-                acc.r[e] += __uint_as_float(ent.y);
+                if (FIRST && i == 0) acc.r[e] = __uint_as_float(ent.y); else acc.r[e] += __uint_as_float(ent.y);
                 inf[e] = ent.x;
             }
         } else {
@@ -102,7 +103,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
                 uint32_t ix = byte_of(sidx, e) & 15u;
                 if (RNG != GC_RNG_NONE) ix |= ((fb[e] >> i) & 1u) << 4;
                 const uint2 ent = s_single[ix];
-                acc.r[e] += __uint_as_float(ent.y);
+                if (FIRST && i == 0) acc.r[e] = __uint_as_float(ent.y); else acc.r[e] += __uint_as_float(ent.y);
                 inf[e] = ent.x;
             }
         }
@@ -115,6 +116,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
         const uint32_t u = prmt(inf[0], inf[1], 0x7362), v = prmt(inf[2], inf[3], 0x7362);
         rows[i] = prmt(u, v, 0x5410);
         if (pair) rows[i + 1] = prmt(u, v, 0x7632);
+        if (FIRST && i == 0) acc.s0w = rows[0];
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -137,6 +139,14 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
     const uint32_t place = tab.place[c0];
 #pragma unroll
     for (int e = 0; e < kEPT; ++e) acc.idx[e] += byte_of(q, e) * place;
+}
+
+// byte B of the four words w[0..3] as one word (byte lane e = w[e])
+template <int B>
+__device__ __forceinline__ uint32_t gather_byte(const uint32_t (&w)[kEPT])
+{
+    constexpr uint32_t sel = 0x4000u | (static_cast<uint32_t>(B) + 4u) << 4 | static_cast<uint32_t>(B);   // (w0.B, w1.B, -, -)
+    return prmt(prmt(w[0], w[1], sel), prmt(w[2], w[3], sel), 0x5410);
 }
 
 template <int N>
@@ -223,6 +233,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         EnvAcc acc;
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.add[e] = 0; acc.orr[e] = 0; acc.first[e] = 0; acc.idx[e] = 0; }
+        acc.s0w = 0;
 
         if (NG == 0) {
             do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
@@ -240,18 +251,19 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                 do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sb, ab, acc);
         }
 
-        uint32_t unsafe_w = 0, count_w = 0;
+        // unsafe / count for the four envs at once (byte lanes): gather the count byte of the info sums,
+        // the presence nibble of the cells j >= 2 and the pair-(0,1) flag (bit 12 = bit 4 of byte 1), pick
+        // the unsafe-levels mask of each env's s'_0 out of tab.unsafe_rows with one byte permute
         float rout[kEPT];
         log2_1p_x4(tab.reward_log2, acc.r, rout);
+        const uint32_t count_w = gather_byte<0>(acc.add) & 0x1F1F1F1Fu;
+        const uint32_t present = gather_byte<1>(acc.orr), flag01 = gather_byte<1>(acc.first);
+        const uint32_t nib = acc.s0w | (acc.s0w >> 4);                        // byte 0: s0_0 | s0_1 << 4, byte 2: s0_2 | s0_3 << 4
+        const uint32_t rowmask = prmt(tab.unsafe_rows, 0u, prmt(nib, 0u, 0x4420) & 0x3333u);
+        const uint32_t unsafe_w = ((((present & rowmask) + 0x0F0F0F0Fu) | flag01) >> 4) & 0x01010101u;
 #pragma unroll
-        for (int e = 0; e < kEPT; ++e) {
-            const uint32_t s0n = (acc.first[e] >> 16) & 3u;
-            const uint32_t rowmask = (tab.unsafe_rows >> (8 * s0n)) & 0xFFu;
-            const uint32_t uns = ((acc.first[e] >> 12) & 1u) | ((((acc.orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
-            const uint32_t cnt = acc.add[e] & 31u;
-            unsafe_w |= uns << (8 * e); count_w |= cnt << (8 * e);
+        for (int e = 0; e < kEPT; ++e)
             if (e < rem) st_reward += __float2int_rn(rout[e] * 16777216.0f);     // |reward| < 128
-        }
         {
             const uint32_t vb = valid_bytes(rem);
             st_steps += rem;
