@@ -34,17 +34,24 @@ namespace {
 #endif
 constexpr int pair_min_blocks(int c, int rng)
 {
-    return (rng == GC_RNG_PHILOX && c > 4) ? 3 : (c < 4 ? GC_PAIR_MINB_NARROW : GC_PAIR_MINB);
+    if (rng == GC_RNG_PHILOX && c > 4) return 3;
+    // deterministic kernels whose 64-register build spills (the cell counts with a ragged or a single
+    // second group): measured faster with the 85-register budget of three blocks
+    // (profiles/r01_tuning_log.md, sweep over all cell counts)
+    if (rng == GC_RNG_NONE && ((c >= 4 && c <= 8) || c == 10 || c == 11)) return GC_PAIR_MINB < 3 ? GC_PAIR_MINB : 3;
+    return c < 4 ? GC_PAIR_MINB_NARROW : GC_PAIR_MINB;
 }
 
-// Everything a thread carries across the cell groups of its four envs.
+// Everything a thread carries across the cell groups of its four envs.  The low halves of the info
+// words (count byte, presence / flag byte) are accumulated two envs per register (16-bit lanes: envs
+// 0, 1 and envs 2, 3): up to 8 pairs of count <= 2 and of presence / flag bytes <= 0x1F never carry
+// out of a lane, so one add per register and pair does the four envs' counts.
 struct EnvAcc {
     float r[kEPT];          // reward sums
-    uint32_t add[kEPT];     // sum of info words: bits 0-4 = counted cells
-    uint32_t orr[kEPT];     // OR of info words of the cells j >= 2: bits 8-11 = levels present
-    uint32_t first[kEPT];   // info word of the pair (cell 0, cell 1) (or of cell 0 alone when C == 1)
+    uint32_t sum01, sum23;  // sums of the info low halves: bits 0-4 of a lane = counted cells
+    uint32_t or01, or23;    // bit 12 of a lane: pair (cell 0, cell 1) is 'unsafe'; bits 8-11: levels present in cells j >= 2
     uint32_t idx[kEPT];     // tabular index
-    uint32_t s0w;           // next level of cell 0 (before an auto-reset), byte lane e = env e
+    uint32_t s0w, s1w;      // next level of cell 0 / cell 1 (before an auto-reset), byte lane e = env e
 };
 
 // One group of N <= 4 consecutive cells starting at cell c0 (c0 % 4 == 0) for the 4 envs of a thread.
@@ -107,16 +114,15 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
                 inf[e] = ent.x;
             }
         }
-#pragma unroll
-        for (int e = 0; e < kEPT; ++e) {
-            acc.add[e] += inf[e];
-            if (FIRST && i == 0) acc.first[e] = inf[e]; else acc.orr[e] |= inf[e];
-        }
+        const uint32_t w01 = prmt(inf[0], inf[1], 0x5410), w23 = prmt(inf[2], inf[3], 0x5410);
+        acc.sum01 += w01; acc.sum23 += w23;
+        const uint32_t keep_bits = (FIRST && i == 0) ? 0x10001000u : 0x0F000F00u;
+        acc.or01 |= w01 & keep_bits; acc.or23 |= w23 & keep_bits;
         // SoA rows of the next state: byte 2 (cell c0+i) and byte 3 (cell c0+i+1) of the four info words
         const uint32_t u = prmt(inf[0], inf[1], 0x7362), v = prmt(inf[2], inf[3], 0x7362);
         rows[i] = prmt(u, v, 0x5410);
         if (pair) rows[i + 1] = prmt(u, v, 0x7632);
-        if (FIRST && i == 0) acc.s0w = rows[0];
+        if (FIRST && i == 0) { acc.s0w = rows[0]; acc.s1w = pair ? rows[1] : rows[0]; }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -126,8 +132,8 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
             uint32_t sew = 0;
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) {
-                const uint32_t s0n = (acc.first[e] >> 16) & 0xFFu;
-                const uint32_t partner = (FIRST && i == 0) ? ((C > 1) ? (acc.first[e] >> 24) : s0n) : byte_of(rows[i], e);
+                const uint32_t s0n = byte_of(acc.s0w, e);
+                const uint32_t partner = (FIRST && i == 0) ? byte_of(acc.s1w, e) : byte_of(rows[i], e);
                 sew |= static_cast<uint32_t>(s_se[c0 + i][(s0n * GC_LVL_PAD + partner) & (GC_TBL - 1)]) << (8 * e);
             }
             st_stream_u32(io.se_row + (c0 + i) * ld + e0, sew);
@@ -139,14 +145,6 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
     const uint32_t place = tab.place[c0];
 #pragma unroll
     for (int e = 0; e < kEPT; ++e) acc.idx[e] += byte_of(q, e) * place;
-}
-
-// byte B of the four words w[0..3] as one word (byte lane e = w[e])
-template <int B>
-__device__ __forceinline__ uint32_t gather_byte(const uint32_t (&w)[kEPT])
-{
-    constexpr uint32_t sel = 0x4000u | (static_cast<uint32_t>(B) + 4u) << 4 | static_cast<uint32_t>(B);   // (w0.B, w1.B, -, -)
-    return prmt(prmt(w[0], w[1], sel), prmt(w[2], w[3], sel), 0x5410);
 }
 
 template <int N>
@@ -232,8 +230,8 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         }
         EnvAcc acc;
 #pragma unroll
-        for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.add[e] = 0; acc.orr[e] = 0; acc.first[e] = 0; acc.idx[e] = 0; }
-        acc.s0w = 0;
+        for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.idx[e] = 0; }
+        acc.sum01 = acc.sum23 = acc.or01 = acc.or23 = acc.s0w = acc.s1w = 0;
 
         if (NG == 0) {
             do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
@@ -251,16 +249,16 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                 do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sb, ab, acc);
         }
 
-        // unsafe / count for the four envs at once (byte lanes): gather the count byte of the info sums,
-        // the presence nibble of the cells j >= 2 and the pair-(0,1) flag (bit 12 = bit 4 of byte 1), pick
-        // the unsafe-levels mask of each env's s'_0 out of tab.unsafe_rows with one byte permute
+        // unsafe / count for the four envs at once (byte lanes): the count and the presence / flag bytes
+        // of the 16-bit lanes, and the unsafe-levels mask of each env's s'_0 picked out of
+        // tab.unsafe_rows with one byte permute (selector nibble e = s'_0 of env e)
         float rout[kEPT];
         log2_1p_x4(tab.reward_log2, acc.r, rout);
-        const uint32_t count_w = gather_byte<0>(acc.add) & 0x1F1F1F1Fu;
-        const uint32_t present = gather_byte<1>(acc.orr), flag01 = gather_byte<1>(acc.first);
+        const uint32_t count_w = prmt(acc.sum01, acc.sum23, 0x6420) & 0x1F1F1F1Fu;
+        const uint32_t present = prmt(acc.or01, acc.or23, 0x7531);            // bits 0-3 levels present, bit 4 pair-(0,1) flag
         const uint32_t nib = acc.s0w | (acc.s0w >> 4);                        // byte 0: s0_0 | s0_1 << 4, byte 2: s0_2 | s0_3 << 4
         const uint32_t rowmask = prmt(tab.unsafe_rows, 0u, prmt(nib, 0u, 0x4420) & 0x3333u);
-        const uint32_t unsafe_w = ((((present & rowmask) + 0x0F0F0F0Fu) | flag01) >> 4) & 0x01010101u;
+        const uint32_t unsafe_w = ((((present & rowmask) + 0x0F0F0F0Fu) | present) >> 4) & 0x01010101u;
 #pragma unroll
         for (int e = 0; e < kEPT; ++e)
             if (e < rem) st_reward += __float2int_rn(rout[e] * 16777216.0f);     // |reward| < 128
