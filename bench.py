@@ -252,8 +252,8 @@ def time_host_path(batches, steps, warmup, dist, device):
     for b in batches:
         ring = [b["ring"][i].cpu().pin_memory() for i in range(2)]
         host_rings.append([(t, t.numpy()) for t in ring])
-    h2d = sum(b["env"].n_cells * b["n"] for b in batches)
-    d2h = sum((b["env"].n_cells + 4 + 4 + 4) * b["n"] for b in batches)
+    h2d = sum(b["env"].host_bytes_per_env_step[0] * b["n"] for b in batches)
+    d2h = sum(b["env"].host_bytes_per_env_step[1] * b["n"] for b in batches)
 
     def one(i):
         sink = 0.0

@@ -538,6 +538,14 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         self._host_np = {k: v.numpy() for k, v in self._host.items()}
 
     @property
+    def host_bytes_per_env_step(self):
+        """(host-to-device, device-to-host) bytes the host path of step() moves per env."""
+        d2h = self.n_cells + 4 + 4 + 2 + (1 if self.max_episode_steps else 0)
+        if self._se_row is not None:
+            d2h += self.n_cells
+        return self.n_cells, d2h
+
+    @property
     def host_action_buffer(self):
         """Pinned int8 [n_cells, num_envs] numpy view: fill it and call step(host_action_buffer)
         to skip the staging copy of the host path."""
@@ -566,9 +574,12 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             self.sync_step_counter()
         torch.cuda.current_stream(self.device).synchronize()     # resident state must be settled
         H = self._host
+        # 'terminated' is constant False (cells3states3actions3.py:122, grid_world.py:113) and 'truncated' is
+        # too without a time limit: their zero-initialised mirrors are returned without a device-to-host copy
         _lib.check(self._lib.gc_step_host(
             self._h, h_actions_ptr, _ptr(H["state"]), _ptr(H["reward"]), _ptr(H["index"]),
-            _ptr(H["terminated"]), _ptr(H["truncated"]), _ptr(H["unsafe"]), _ptr(H["count"]), _ptr(H.get("se_row")),
+            None, _ptr(H["truncated"]) if self.max_episode_steps else None, _ptr(H["unsafe"]), _ptr(H["count"]),
+            _ptr(H.get("se_row")),
             _ptr(self._actions), _ptr(self._state), _ptr(self._t), _ptr(self._reward), _ptr(self._index),
             _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
             _ptr(self._se_row), _ptr(self._stats), self.host_chunk_envs))
