@@ -11,13 +11,17 @@
 namespace {
 
 
-// One fat block per SM: the 40 KB table is staged once per SM instead of once per 256 threads, which
-// matters for launches of a few million envs where staging traffic rivals the useful traffic.
+// Two blocks of 512 threads per SM: the 40 KB table is staged twice per SM instead of once per 256
+// threads (staging traffic rivals the useful traffic for launches of a few million envs), and a block
+// that drains frees half an SM, so that a kernel of another handle running on a second stream (the mixed
+// workload: polarisation and grid world stepped concurrently) can move in.  Measured on that workload:
+// 1024 x 1 -> 0.77, 256 x 4 -> 0.80, 384 x 2 -> 0.82, 512 x 2 -> 0.86 of the HBM roofline
+// (profiles/r01_tuning_log.md); alone the geometries are within 2 % of each other.
 #ifndef GC_GRID_THREADS
-#define GC_GRID_THREADS 1024
+#define GC_GRID_THREADS 512
 #endif
 #ifndef GC_GRID_MINB
-#define GC_GRID_MINB 1
+#define GC_GRID_MINB 2
 #endif
 constexpr int kGridThreads = GC_GRID_THREADS;
 // largest index the masked inputs can form: (31 + 20 * 31) * 25 + 7 + 5 * 7, rounded up
