@@ -173,19 +173,12 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     __shared__ uint8_t s_se[WITH_SE ? C : 1][GC_TBL];
     __shared__ unsigned long long s_stats[5];
 
-    for (int i = threadIdx.x; i < N_PAIR; i += kThreads) s_pair[i] = lut[i];
-    if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
-    if (WITH_SE)
-        for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
-    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
-    __syncthreads();
+    __shared__ StepCounterShared s_ctr;
 
-    const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? launch_step_counter(io) : 0u;
-    uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;   // < 2^32 per thread and launch
-    long long st_reward = 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
     // Narrow envs (C < 4: a thread reads only ~10 words per 4 envs) prefetch the inputs of their next
-    // 4-env word before computing the current one, to keep enough bytes in flight per SM.
+    // 4-env word before computing the current one, to keep enough bytes in flight per SM; the first
+    // word's inputs are requested before the tables are staged, so that the two latencies overlap.
 #ifndef GC_PAIR_PREFETCH_WIDE
 #define GC_PAIR_PREFETCH_WIDE 0
 #endif
@@ -198,6 +191,18 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         load_cells<G0>(io, 0, e0, ps, pa);
         pt = ld_stream_v4(io.t + e0);
     }
+    step_counter_read(io, &s_ctr);
+    for (int i = threadIdx.x; i < N_PAIR; i += kThreads) s_pair[i] = lut[i];
+    if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
+    if (WITH_SE)
+        for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+
+    const uint32_t step_now = step_counter_arrive(io, &s_ctr);
+    const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? step_now : 0u;
+    uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;   // < 2^32 per thread and launch
+    long long st_reward = 0;
     for (; e0 < io.end; e0 += stride) {
         const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);    // envs of this word in range
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);           // multiple of 4: | e never carries
@@ -282,7 +287,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         const ThreadStats ts = {st_steps, st_unsafe, st_count, st_trunc, st_reward};
         block_flush_stats(ts, s_stats, io.stats);
     }
-    tick_step_counter(io);
+    step_counter_finish(io, &s_ctr);
 }
 
 template <int C, int RNG>

@@ -86,6 +86,35 @@ __device__ __forceinline__ void tick_step_counter(const uint32_t *step_ctr, uint
 
 __device__ __forceinline__ void tick_step_counter(const StepIO &io) { tick_step_counter(io.step_ctr, io.done_ctr, 1u); }
 
+// The same protocol with the arrival moved to the START of the kernel, so that no atomic round trip and
+// no barrier sit on the kernel's tail (they are ~1 us of a launch-bound 4 us step):
+//   step_counter_read    before the block's first __syncthreads: thread 0 copies the counter to shared
+//                        memory (the store needs the loaded value, so the load has completed at the barrier)
+//   step_counter_arrive  after that barrier: thread 0 arrives; every thread gets the step from shared memory
+//   step_counter_finish  at kernel exit: the block that arrived last advances the counter.
+// Every block has read the counter before it arrives, so when the last arrival is known nobody of this
+// launch reads the counter any more; the next launch starts after this one has completed.
+struct StepCounterShared { uint32_t step, arrived; };
+
+__device__ __forceinline__ void step_counter_read(const StepIO &io, StepCounterShared *s)
+{
+    if (threadIdx.x == 0) s->step = launch_step_counter(io);
+}
+
+__device__ __forceinline__ uint32_t step_counter_arrive(const StepIO &io, StepCounterShared *s)
+{
+    if (threadIdx.x == 0 && io.step_ctr != nullptr) s->arrived = atomicAdd(io.done_ctr, 1u);
+    return s->step;
+}
+
+__device__ __forceinline__ void step_counter_finish(const StepIO &io, const StepCounterShared *s)
+{
+    if (threadIdx.x == 0 && io.step_ctr != nullptr && s->arrived == gridDim.x - 1) {
+        *io.done_ctr = 0u;
+        *const_cast<uint32_t *>(io.step_ctr) = s->step + 1u;
+    }
+}
+
 // log2(1 + r) of the `nonlinear` rewards (np.log2(1 + .), cells3states3actions3.py:47-49) to ~4e-7
 // relative: for -1/2 <= r <= 1 (always, for the reference's 2- and 3-cell envs) 2 atanh(s) / ln 2 with
 // s = r / (2 + r), |s| <= 1/3, as a degree-6 polynomial in s^2 with 2 / ln 2 folded into the

@@ -34,6 +34,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
 {
     extern __shared__ __align__(16) uint32_t s_lut[];          // kGridLutAlloc entries, the first 10,000 staged
     __shared__ unsigned long long s_stats[5];
+    __shared__ StepCounterShared s_ctr;
     const int64_t ld = io.ld;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
     // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
@@ -48,6 +49,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         p_a0 = ld_stream_u32(io.actions + e0); p_a1 = ld_stream_u32(io.actions + ld + e0);
         p_t = ld_stream_v4(io.t + e0);
     }
+    step_counter_read(io, &s_ctr);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
@@ -56,7 +58,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
 
-    const uint32_t step_counter = launch_step_counter(io);
+    const uint32_t step_counter = step_counter_arrive(io, &s_ctr);
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     for (; e0 < io.end; e0 += stride) {
         const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
@@ -191,7 +193,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         const ThreadStats ts = {st_steps, 0, st_count, st_trunc, static_cast<long long>(st_reward) << 24};
         block_flush_stats(ts, s_stats, io.stats);
     }
-    tick_step_counter(io);
+    step_counter_finish(io, &s_ctr);
 }
 
 }  // namespace
