@@ -63,6 +63,9 @@ class ClockSampler:
 
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
     NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80}
+    # NVML queries go through the driver and slow concurrent kernel launches down: polled every 5 ms they
+    # doubled the per-step time of the launch-bound workloads (15 us against 6-7 us per step)
+    PERIOD_S = 0.05
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
@@ -106,7 +109,7 @@ class ClockSampler:
                 self._poll_once()
             except Exception:
                 pass
-            time.sleep(0.005)
+            self._stop.wait(self.PERIOD_S)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -156,14 +159,9 @@ def build_batches(workload, device, rank, n_override=None, env_scale=1.0):
             else:
                 a = torch.randint(0, env.n_actions, (env.n_cells, env.ld), dtype=torch.int8, device=device, generator=gen)
             ring.append(a)
-        batches.append(dict(env=env, ring=ring, kind=kind, n=n, bytes=bytes_per_env_step(kind, env.n_cells),
-                            calls=[env.bind_step(a) for a in ring]))
+        batches.append(dict(env=env, ring=ring, kind=kind, n=n, bytes=bytes_per_env_step(kind, env.n_cells)))
     return batches
 
-
-def launch_step(batch, i):
-    """One device-path step: actions already resident; a single ctypes call = a single kernel."""
-    batch["calls"][i % RING]()
 
 
 def time_device_path(batches, steps, warmup, dist, device, sampler_index):
@@ -173,15 +171,16 @@ def time_device_path(batches, steps, warmup, dist, device, sampler_index):
     import torch
     main = torch.cuda.current_stream(device)
     streams = [main] if len(batches) == 1 else [torch.cuda.Stream(device=device) for _ in batches]
+    # one device-path step = one pre-bound ctypes call = one kernel, on the sub-batch's own stream
+    calls = [[b["env"].bind_step(a, stream=s) for a in b["ring"]] for b, s in zip(batches, streams)]
 
     def run(lo, hi):
         for s in streams:
             if s is not main:
                 s.wait_stream(main)
         for i in range(lo, hi):
-            for b, s in zip(batches, streams):
-                with torch.cuda.stream(s):
-                    launch_step(b, i)
+            for c in calls:
+                c[i % RING]()
         for s in streams:
             if s is not main:
                 main.wait_stream(s)
