@@ -337,6 +337,76 @@ def test_cuda_graph_replay_advances_rng(B, O):
     assert env.stats()["env_steps"] == 26 * n
 
 
+def test_cuda_graph_replay_stochastic_polarisation(B, O):
+    """The same for the pair-table kernel (global-step counter: blocks arrive at kernel start, the last
+    one advances it), small and multi-wave batches."""
+    for n in (300, 700001):
+        rng = np.random.default_rng(n)
+        acts = rng.integers(0, 3, size=(8, 3, n)).astype(np.int8)
+        env = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=5, rng_episodic=False, noise_prob=0.3)
+        ora = O.OracleEnv(n_envs=n, noise=True, rng_episodic=False, seed=5, noise_prob=0.3, reward="nonlinear_rp")
+        ring = []
+        for k in range(8):
+            a = torch.zeros(3, env.ld, dtype=torch.int8, device="cuda")
+            a[:, :n] = dev(acts[k])
+            ring.append(a)
+        graph = env.capture_steps(ring)
+        for rep in range(2):
+            graph.replay()
+            for k in range(8):
+                ora.step(acts[k])
+            assert_matches_oracle(env, ora, check_se=True)
+        assert env.sync_step_counter() == 16
+
+
+def test_bound_step_on_pinned_stream(B, O):
+    """bind_step(stream=s): launches go to s whatever stream is current; two handles on two streams."""
+    n = 40000
+    rng = np.random.default_rng(12)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    env = B.CellularVectorEnv(num_envs=n, stochastic=True, env_seed=2)
+    ora = O.OracleEnv(n_envs=n, noise=True, rng_episodic=True, seed=2, reward="nonlinear_rp")
+    gw = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=3, max_episode_steps=6)
+    gwo = O.OracleEnv(kind="gridworld", n_envs=n, seed=3, max_episode_steps=6)
+    a1 = torch.zeros(3, env.ld, dtype=torch.int8, device="cuda")
+    a2 = torch.full((2, gw.ld), 4, dtype=torch.int8, device="cuda")
+    c1, c2 = env.bind_step(a1, stream=s1), gw.bind_step(a2, stream=s2)
+    for t in range(10):
+        x1 = rng.integers(0, 3, size=(3, n)).astype(np.int8)
+        x2 = np.full((2, n), 4, np.int8)
+        x2[rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+        a1[:, :n] = dev(x1)
+        a2[:, :n] = dev(x2)
+        s1.wait_stream(torch.cuda.current_stream())
+        s2.wait_stream(torch.cuda.current_stream())
+        c1()
+        c2()
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        ora.step(x1)
+        gwo.step(x2)
+    assert_matches_oracle(env, ora)
+    assert_matches_oracle(gw, gwo)
+    with pytest.raises(ValueError):
+        env.bind_step(torch.zeros(3, 8, dtype=torch.int8, device="cuda"), stream=s1)
+
+
+def test_zero_noise_probability_is_the_deterministic_env(B, O):
+    """noise_prob = 0 dispatches the draw-free kernels; the deadlock rule still applies."""
+    n = 5000
+    rng = np.random.default_rng(1)
+    for C, S in ((3, 3), (9, 4)):
+        env = B.CellularVectorEnv(num_envs=n, n_cells=C, n_states=S, stochastic=True, deadlock=True, noise_prob=0.0, env_seed=1)
+        ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, noise=True, deadlock=True, rng_episodic=True, seed=1,
+                          noise_prob=0.0, reward="nonlinear_rp")
+        for t in range(12):
+            a = rng.integers(0, S, size=(C, n)).astype(np.int8)
+            env.step_device(dev(a))
+            ora.step(a)
+        assert_matches_oracle(env, ora)
+        assert bool((env.state == S - 1).any())
+
+
 def test_shard_invariance(B):
     """Results for env i do not depend on which shard owns it (Philox keyed by global env id)."""
     n, T = 40000, 12
