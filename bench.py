@@ -486,8 +486,9 @@ def main():
         run_reference_arm(args, args.workload)
         return
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    # NCCL logs to stdout by default (version banner at VERSION / WARN, everything at INFO): send whatever
+    # level the caller asked for to stderr, so that stdout stays the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
