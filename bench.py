@@ -422,16 +422,27 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
     ro_res = None
     if dist is None:                       # K-step fused rollout (random actions generated in the kernel)
         K = 64
-        for b in batches:
-            b["env"].rollout(K)
+        main = torch.cuda.current_stream(device)
+        ro_streams = [main] if len(batches) == 1 else [torch.cuda.Stream(device=device) for _ in batches]
+
+        def rollouts(reps):                # independent sub-batches on one stream each, as in the step path
+            for s in ro_streams:
+                if s is not main:
+                    s.wait_stream(main)
+            for _ in range(reps):
+                for b, s in zip(batches, ro_streams):
+                    with torch.cuda.stream(s):
+                        b["env"].rollout(K)
+            for s in ro_streams:
+                if s is not main:
+                    main.wait_stream(s)
+        rollouts(1)
         torch.cuda.synchronize(device)
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 4
-        r0.record()
-        for _ in range(reps):
-            for b in batches:
-                b["env"].rollout(K)
-        r1.record()
+        r0.record(main)
+        rollouts(reps)
+        r1.record(main)
         r1.synchronize()
         ro_res = {"value": n_rank * K * reps / (r0.elapsed_time(r1) * 1e-3), "steps_per_launch": K,
                   "note": "fused rollout: state in registers, actions generated in-kernel (not per-step step())"}

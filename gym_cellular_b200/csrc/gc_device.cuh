@@ -202,7 +202,10 @@ __device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigne
 }
 
 // ---------------------------------------------------------------------------------------------
-// Launch geometry: one wave of resident blocks (SM count x occupancy), grid-stride inside.
+// Launch geometry: GC_OVERSUB waves of resident blocks (SM count x occupancy), grid-stride inside.
+#ifndef GC_OVERSUB
+#define GC_OVERSUB 1
+#endif
 template <auto Kernel, int THREADS = kThreads>
 int grid_for(int64_t n_envs, int n_sm)
 {
@@ -212,7 +215,7 @@ int grid_for(int64_t n_envs, int n_sm)
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, 0) != cudaSuccess || per_sm < 1))
         per_sm = 1;
     const int64_t need = (n_envs + THREADS * kEPT - 1) / (THREADS * kEPT);
-    const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;
+    const int64_t cap = static_cast<int64_t>(n_sm) * per_sm * GC_OVERSUB;
     return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 

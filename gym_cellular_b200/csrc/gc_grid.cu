@@ -23,6 +23,9 @@ namespace {
 #ifndef GC_GRID_MINB
 #define GC_GRID_MINB 2
 #endif
+#ifndef GC_GRID_OVERSUB
+#define GC_GRID_OVERSUB 1
+#endif
 constexpr int kGridThreads = GC_GRID_THREADS;
 // largest index the masked inputs can form: (31 + 20 * 31) * 25 + 7 + 5 * 7, rounded up
 constexpr int kGridLutAlloc = ((31 + 20 * 31) * 25 + 42 + 1 + 3) / 4 * 4;
@@ -209,7 +212,7 @@ int grid_blocks(int64_t n, int n_sm, cudaError_t *err)
             per_sm = 1;
     }
     const int64_t need = (n + kGridThreads * kEPT - 1) / (kGridThreads * kEPT);
-    const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;
+    const int64_t cap = static_cast<int64_t>(n_sm) * per_sm * GC_GRID_OVERSUB;
     return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 

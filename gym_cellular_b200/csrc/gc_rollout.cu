@@ -171,13 +171,14 @@ cell_rollout_kernel(const __grid_constant__ CellTables tab, const __grid_constan
             }
             // ---- bookkeeping --------------------------------------------------------------------
             uint32_t keep = 0xFFFFFFFFu, unsafe_w = 0, count_w = 0, trunc_w = 0;
+            float rlog[kEPT];
+            log2_1p_x4(tab.reward_log2, r, rlog);
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) {
                 const uint32_t s0n = (first[e] >> 16) & 3u;
                 const uint32_t rowmask = (tab.unsafe_rows >> (8 * s0n)) & 0xFFu;
                 const uint32_t uns = ((first[e] >> 12) & 1u) | ((((orr[e] >> 8) & rowmask) != 0u) ? 1u : 0u);
-                float rr = r[e];
-                if (tab.reward_log2) rr = log2_1p(rr);
+                const float rr = rlog[e];
                 ret[e] += rr;
                 nuns[e] += uns;
                 unsafe_w |= uns << (8 * e); count_w |= (add[e] & 31u) << (8 * e);
