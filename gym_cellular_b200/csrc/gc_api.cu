@@ -218,8 +218,9 @@ int gc_create(const gc_config *cfg, gc_env **out)
         if (!lut) e = cudaErrorMemoryAllocation;
         if (e == cudaSuccess) {
             gc_build_grid_lut(lut.get());
-            e = cudaMalloc(&d_lut, GC_GRID_LUT_ENTRIES * sizeof(uint32_t));
+            e = cudaMalloc(&d_lut, GC_GRID_LUT_ALLOC * sizeof(uint32_t));
         }
+        if (e == cudaSuccess) e = cudaMemset(d_lut, 0, GC_GRID_LUT_ALLOC * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaMemcpy(d_lut, lut.get(), GC_GRID_LUT_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice);
         env->grid.lut = d_lut;
     }

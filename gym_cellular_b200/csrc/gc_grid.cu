@@ -23,19 +23,25 @@ namespace {
 #ifndef GC_GRID_MINB
 #define GC_GRID_MINB 2
 #endif
+// Launches of up to GC_GRID_SMALL_ITERS 4-env words per thread read the table through L1 (`ld.global.nc`)
+// instead of staging it: the staging phase (40 KB per block, serial with the block's work) is ~1 us of
+// an 8 us launch there, while for long launches the shared-memory copy is the faster lookup
+// (profiles/r01_tuning_log.md: 2^20 envs 130 -> 145 G env-steps/s in a CUDA graph, 2^22 envs 0.866 -> 0.841).
+#ifndef GC_GRID_SMALL_ITERS
+#define GC_GRID_SMALL_ITERS 3
+#endif
 #ifndef GC_GRID_OVERSUB
 #define GC_GRID_OVERSUB 1
 #endif
 constexpr int kGridThreads = GC_GRID_THREADS;
-// largest index the masked inputs can form: (31 + 20 * 31) * 25 + 7 + 5 * 7, rounded up
-constexpr int kGridLutAlloc = ((31 + 20 * 31) * 25 + 42 + 1 + 3) / 4 * 4;
+constexpr int kGridLutAlloc = GC_GRID_LUT_ALLOC;
 constexpr int kGridSmemBytes = kGridLutAlloc * 4;
 
-template <int RNG>
+template <int RNG, bool LUT_GLOBAL>
 __global__ void __launch_bounds__(kGridThreads, GC_GRID_MINB)
 grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ StepIO io)
 {
-    extern __shared__ __align__(16) uint32_t s_lut[];          // kGridLutAlloc entries, the first 10,000 staged
+    extern __shared__ __align__(16) uint32_t s_lut[];          // kGridLutAlloc entries, the first 10,000 staged (unless LUT_GLOBAL)
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const int64_t ld = io.ld;
@@ -53,7 +59,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         p_t = ld_stream_v4(io.t + e0);
     }
     step_counter_read(io, &s_ctr);
-    {
+    if (!LUT_GLOBAL) {
         const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
         for (int i = threadIdx.x; i < GC_GRID_LUT_ENTRIES / 4; i += kGridThreads) dst[i] = src[i];
@@ -84,8 +90,13 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         const uint32_t i02 = ((s0m & 0x00FF00FFu) + 20u * (s1m & 0x00FF00FFu)) * 25u + (actw & 0x00FF00FFu);
         const uint32_t i13 = (((s0m >> 8) & 0x00FF00FFu) + 20u * ((s1m >> 8) & 0x00FF00FFu)) * 25u + ((actw >> 8) & 0x00FF00FFu);
         uint32_t ent[kEPT];
-        ent[0] = s_lut[i02 & 0xFFFFu]; ent[1] = s_lut[i13 & 0xFFFFu];
-        ent[2] = s_lut[i02 >> 16]; ent[3] = s_lut[i13 >> 16];
+        if (LUT_GLOBAL) {
+            ent[0] = __ldg(gp.lut + (i02 & 0xFFFFu)); ent[1] = __ldg(gp.lut + (i13 & 0xFFFFu));
+            ent[2] = __ldg(gp.lut + (i02 >> 16)); ent[3] = __ldg(gp.lut + (i13 >> 16));
+        } else {
+            ent[0] = s_lut[i02 & 0xFFFFu]; ent[1] = s_lut[i13 & 0xFFFFu];
+            ent[2] = s_lut[i02 >> 16]; ent[3] = s_lut[i13 >> 16];
+        }
         // Seed dispersal (grid_world.py:160-162): unless both jurisdictions were barren, one uniform
         // draw; below dispersal_prob the 2x2 bits and the jurisdiction index are drawn as well.  The
         // trigger words of the four envs of a thread are the four words of ONE Philox block (keyed by
@@ -202,13 +213,13 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
 }  // namespace
 
 template <auto Kernel>
-int grid_blocks(int64_t n, int n_sm, cudaError_t *err)
+int grid_blocks(int64_t n, int n_sm, int smem_bytes, cudaError_t *err)
 {
     static int per_sm = 0;
     if (per_sm == 0) {
         *err = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGridSmemBytes);
         if (*err != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kGridThreads, kGridSmemBytes) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kGridThreads, smem_bytes) != cudaSuccess || per_sm < 1)
             per_sm = 1;
     }
     const int64_t need = (n + kGridThreads * kEPT - 1) / (kGridThreads * kEPT);
@@ -216,18 +227,27 @@ int grid_blocks(int64_t n, int n_sm, cudaError_t *err)
     return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 
-cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
+template <int RNG>
+cudaError_t launch_grid(const GridParams &gp, const StepIO &io, int n_sm, cudaStream_t st)
 {
     const int64_t n = io.end - io.begin;
     cudaError_t err = cudaSuccess;
-    if (rng_mode == GC_RNG_REPLAY) {
-        const int g = grid_blocks<grid_step_kernel<GC_RNG_REPLAY>>(n, n_sm, &err);
+    // words per thread if the table-staging kernel's one wave of blocks were launched
+    const int64_t wave = static_cast<int64_t>(n_sm) * GC_GRID_MINB * kGridThreads * kEPT;
+    if (n <= wave * GC_GRID_SMALL_ITERS) {
+        const int g = grid_blocks<grid_step_kernel<RNG, true>>(n, n_sm, 0, &err);
         if (err != cudaSuccess) return err;
-        grid_step_kernel<GC_RNG_REPLAY><<<g, kGridThreads, kGridSmemBytes, st>>>(gp, io);
+        grid_step_kernel<RNG, true><<<g, kGridThreads, 0, st>>>(gp, io);
     } else {
-        const int g = grid_blocks<grid_step_kernel<GC_RNG_PHILOX>>(n, n_sm, &err);
+        const int g = grid_blocks<grid_step_kernel<RNG, false>>(n, n_sm, kGridSmemBytes, &err);
         if (err != cudaSuccess) return err;
-        grid_step_kernel<GC_RNG_PHILOX><<<g, kGridThreads, kGridSmemBytes, st>>>(gp, io);
+        grid_step_kernel<RNG, false><<<g, kGridThreads, kGridSmemBytes, st>>>(gp, io);
     }
     return cudaGetLastError();
+}
+
+cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
+{
+    return rng_mode == GC_RNG_REPLAY ? launch_grid<GC_RNG_REPLAY>(gp, io, n_sm, st)
+                                     : launch_grid<GC_RNG_PHILOX>(gp, io, n_sm, st);
 }

@@ -83,6 +83,10 @@ struct GridParams {
 
 // Grid-world transition table: entry index = (code_0 + 20 * code_1) * 25 + (a_0 + 5 * a_1)
 #define GC_GRID_LUT_ENTRIES (400 * 25)
+// largest index the kernels' masked inputs (5-bit codes, 3-bit actions) can form, (31 + 20 * 31) * 25 + 7 + 5 * 7,
+// rounded up: the device table and its shared-memory copy are this long (zero padding beyond the 10,000
+// entries), so that out-of-range inputs -- never produced by the kernels -- read padding, not foreign memory
+#define GC_GRID_LUT_ALLOC (((31 + 20 * 31) * 25 + 42 + 1 + 3) / 4 * 4)
 // entry layout: byte 0 next code_0, byte 1 next code_1, bits 16-17 reward (trees that died),
 // bits 18-19 barren jurisdictions before the step, bit 20 / 21 row-0 side effects [0][0] / [0][1]
 // == 'safe', bit 22 the action names no position although an agent exists (reference: KeyError)
