@@ -119,29 +119,39 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
                 }
             }
         }
+        if (RNG == GC_RNG_PHILOX) {
+            // One test for the four envs (the event has probability 0.01 per env-step), then per env: the
+            // drawn 2x2 bits (times tree_positions) replace jurisdiction k's trees (:162); reward and the
+            // side-effect bits of the entry are redone from the packed tree masks (byte 0 / byte 1).
+            // Given the trigger (word < p * 2^32) the low bits of the word are uniform up to 2^-25: they
+            // serve as the three binary draws that matter, b00 = bit 0, b10 = bit 1, k = bit 2.
+            const uint32_t thr = gp.dispersal_thr_m1;
+            if (gp.dispersal_thr_nz && (trig[0] <= thr || trig[1] <= thr || trig[2] <= thr || trig[3] <= thr)) {
 #pragma unroll
-        for (int e = 0; e < kEPT; ++e) {
-            const uint32_t nb = (ent[e] >> 18) & 3u;
-            if (nb < 2u) {
-                const bool valid = e < rem;
-                bool trigger;
-                uint32_t b00 = 0, b10 = 0, k = 0;
-                if (RNG == GC_RNG_REPLAY) {
-                    const double *u = io.replay + (valid ? (e0 + e) * 6 : 0);
-                    trigger = valid && (u[0] < gp.dispersal_prob);
-                    b00 = static_cast<uint32_t>(u[1] * 2.0);
-                    b10 = static_cast<uint32_t>(u[3] * 2.0);
-                    k = static_cast<uint32_t>(u[5] * 2.0);
-                } else {
-                    trigger = gp.dispersal_thr_nz && (trig[e] <= gp.dispersal_thr_m1);
-                }
-                if (trigger) {
-                    if (RNG == GC_RNG_PHILOX) {
-                        // given the trigger (word < p * 2^32) the low bits of the word are uniform up
-                        // to 2^-25: they serve as the three binary draws that matter (b00, b10, k)
-                        b00 = trig[e] & 1u; b10 = (trig[e] >> 1) & 1u; k = (trig[e] >> 2) & 1u;
+                for (int e = 0; e < kEPT; ++e) {
+                    uint32_t x = ent[e];
+                    const uint32_t w = trig[e];
+                    if (w <= thr && ((x >> 18) & 3u) < 2u) {
+                        const uint32_t Nk = ((w >> 1) & 1u) | ((w & 1u) << 1);
+                        const uint32_t sh = (w & 4u) << 1;                               // 8 k
+                        x = (x & ~(3u << sh)) | (Nk << sh);
+                        const uint32_t Tp = (byte_of(s0w, e) & 3u) | ((byte_of(s1w, e) & 3u) << 8);
+                        const uint32_t Np = x & 0x0303u;
+                        const uint32_t rew = __popc(Tp & ~Np);
+                        const uint32_t se1 = (Np & 3u) ? 1u : 0u, se0 = (se1 && (Np & 0x0300u)) ? 1u : 0u;
+                        ent[e] = (x & ~((3u << 16) | (3u << 20))) | (rew << 16) | (se0 << 20) | (se1 << 21);
                     }
-                    // the drawn 2x2 bits (times tree_positions) replace jurisdiction k's trees: :162
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                const uint32_t nb = (ent[e] >> 18) & 3u;
+                const bool valid = e < rem;
+                const double *u = io.replay + (valid ? (e0 + e) * 6 : 0);
+                if (nb < 2u && valid && u[0] < gp.dispersal_prob) {
+                    const uint32_t b00 = static_cast<uint32_t>(u[1] * 2.0), b10 = static_cast<uint32_t>(u[3] * 2.0);
+                    const uint32_t k = static_cast<uint32_t>(u[5] * 2.0);
                     const uint32_t T0 = byte_of(s0w, e) & 3u, T1 = byte_of(s1w, e) & 3u;
                     uint32_t nc0 = ent[e] & 0xFFu, nc1 = (ent[e] >> 8) & 0xFFu;
                     const uint32_t Nk = b10 | (b00 << 1);
