@@ -50,7 +50,7 @@ __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v)
 __device__ __forceinline__ int4 ld_stream_v4(const void *p) { return __ldcs(reinterpret_cast<const int4 *>(p)); }
 __device__ __forceinline__ void st_stream_v4(void *p, int4 v) { __stcs(reinterpret_cast<int4 *>(p), v); }
 
-// Per-thread statistics, reduced once per block at kernel exit: warp shuffles, one shared-memory
+// Per-thread statistics, reduced once per block at kernel exit: REDUX.SUM over the warp, one shared-memory
 // atomic per warp, one global atomic per block and statistic.
 struct ThreadStats {
     uint32_t steps, unsafe, count, truncated;     // per thread and launch: < 2^32
