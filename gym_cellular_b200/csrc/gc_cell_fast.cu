@@ -185,6 +185,15 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     constexpr bool PREFETCH = NG == 0 || GC_PAIR_PREFETCH_WIDE;
     constexpr int G0 = NG > 0 ? 4 : R;                       // cells in the first group
     int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+    // the immutable tables are requested first (they may be read while the previous step kernel of the
+    // stream is still running), then the data the previous kernel wrote, then the tables are stored
+    constexpr int LUT_PER_THREAD = N_PAIR / kThreads;
+    uint2 lut_pair[LUT_PER_THREAD], lut_single = make_uint2(0u, 0u);
+#pragma unroll
+    for (int k = 0; k < LUT_PER_THREAD; ++k) lut_pair[k] = lut[threadIdx.x + k * kThreads];
+    if (threadIdx.x < N_SINGLE) lut_single = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
+    pdl_launch_dependents();
+    pdl_wait();
     uint32_t ps[4], pa[4];
     int4 pt = make_int4(0, 0, 0, 0);
     if constexpr (PREFETCH) if (e0 < io.end) {
@@ -192,8 +201,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         pt = ld_stream_v4(io.t + e0);
     }
     step_counter_read(io, &s_ctr);
-    for (int i = threadIdx.x; i < N_PAIR; i += kThreads) s_pair[i] = lut[i];
-    if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < LUT_PER_THREAD; ++k) s_pair[threadIdx.x + k * kThreads] = lut_pair[k];
+    if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut_single;
     if (WITH_SE)
         for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
@@ -295,9 +305,9 @@ cudaError_t launch_pair_cr(const CellTables &tab, const StepIO &io, const uint2 
 {
     const int64_t n = io.end - io.begin;
     if (io.se_row)
-        cell_pair_kernel<C, RNG, true><<<grid_for<cell_pair_kernel<C, RNG, true>>(n, n_sm), kThreads, 0, st>>>(tab, io, lut);
+        return launch_step_kernel(cell_pair_kernel<C, RNG, true>, grid_for<cell_pair_kernel<C, RNG, true>>(n, n_sm), kThreads, 0, st, tab, io, lut);
     else
-        cell_pair_kernel<C, RNG, false><<<grid_for<cell_pair_kernel<C, RNG, false>>(n, n_sm), kThreads, 0, st>>>(tab, io, lut);
+        return launch_step_kernel(cell_pair_kernel<C, RNG, false>, grid_for<cell_pair_kernel<C, RNG, false>>(n, n_sm), kThreads, 0, st, tab, io, lut);
     return cudaGetLastError();
 }
 

@@ -1,6 +1,8 @@
 // Device-side helpers shared by the kernel translation units.
 #pragma once
 #include "gc_internal.h"
+#include <cstdlib>
+#include <utility>
 
 namespace {
 
@@ -199,6 +201,38 @@ __device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigne
     }
     __syncthreads();
     if (threadIdx.x < 5 && s_stats[threadIdx.x]) atomicAdd(&g_stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: consecutive step kernels of a stream (or of a captured graph) are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that kernel N+1 becomes resident
+// while kernel N drains and overlaps its launch latency and table loads with N's tail.  Everything that
+// N may still be writing (state, t, step counter, statistics) is touched only after pdl_wait(), which
+// returns once all preceding kernels of the stream have completed and flushed; only the immutable
+// tables are read before it.  Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled()
+{
+    static const bool on = [] { const char *v = std::getenv("GC_B200_PDL"); return !(v && v[0] == '0'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_step_kernel(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // ---------------------------------------------------------------------------------------------

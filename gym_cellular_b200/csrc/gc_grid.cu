@@ -51,6 +51,21 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).  The first word's inputs are
     // requested before the table is staged, so that the two latencies overlap.
     int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x) * kEPT;
+    // the immutable table is requested first (possibly while the previous step kernel of the stream is
+    // still running: gc_device.cuh, programmatic dependent launch), then the first word's inputs, then
+    // the table is stored to shared memory, so that the two latencies overlap
+    constexpr int LUT_VEC = GC_GRID_LUT_ENTRIES / 4, LUT_PER_THREAD = (LUT_VEC + kGridThreads - 1) / kGridThreads;
+    uint4 lut_reg[LUT_GLOBAL ? 1 : LUT_PER_THREAD];
+    if (!LUT_GLOBAL) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
+#pragma unroll
+        for (int k = 0; k < LUT_PER_THREAD; ++k) {
+            const int i = threadIdx.x + k * kGridThreads;
+            if (i < LUT_VEC) lut_reg[k] = src[i];
+        }
+    }
+    pdl_launch_dependents();
+    pdl_wait();
     uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;
     int4 p_t = make_int4(0, 0, 0, 0);
     if (e0 < io.end) {
@@ -60,9 +75,12 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     }
     step_counter_read(io, &s_ctr);
     if (!LUT_GLOBAL) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (int i = threadIdx.x; i < GC_GRID_LUT_ENTRIES / 4; i += kGridThreads) dst[i] = src[i];
+#pragma unroll
+        for (int k = 0; k < LUT_PER_THREAD; ++k) {
+            const int i = threadIdx.x + k * kGridThreads;
+            if (i < LUT_VEC) dst[i] = lut_reg[k];
+        }
     }
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     __syncthreads();
@@ -247,11 +265,11 @@ cudaError_t launch_grid(const GridParams &gp, const StepIO &io, int n_sm, cudaSt
     if (n <= wave * GC_GRID_SMALL_ITERS) {
         const int g = grid_blocks<grid_step_kernel<RNG, true>>(n, n_sm, 0, &err);
         if (err != cudaSuccess) return err;
-        grid_step_kernel<RNG, true><<<g, kGridThreads, 0, st>>>(gp, io);
+        return launch_step_kernel(grid_step_kernel<RNG, true>, g, kGridThreads, 0, st, gp, io);
     } else {
         const int g = grid_blocks<grid_step_kernel<RNG, false>>(n, n_sm, kGridSmemBytes, &err);
         if (err != cudaSuccess) return err;
-        grid_step_kernel<RNG, false><<<g, kGridThreads, kGridSmemBytes, st>>>(gp, io);
+        return launch_step_kernel(grid_step_kernel<RNG, false>, g, kGridThreads, kGridSmemBytes, st, gp, io);
     }
     return cudaGetLastError();
 }
