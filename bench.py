@@ -497,8 +497,13 @@ def main():
         run_reference_arm(args, args.workload)
         return
 
-    # NCCL logs to stdout by default (version banner at VERSION / WARN, everything at INFO): send whatever
-    # level the caller asked for to stderr, so that stdout stays the one JSON line
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1 behind
+    # Python's back (NCCL prints its version banner there, and its log at NCCL_DEBUG=INFO) are sent to
+    # stderr by pointing descriptor 1 at it; Python's own sys.stdout keeps the original descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
