@@ -243,6 +243,21 @@ def test_other_shapes(B, O, C, S):
     _rollout(env, ora, 10, np.random.default_rng(C))
 
 
+@pytest.mark.parametrize("C", list(range(1, 17)))
+def test_every_cell_count_deterministic_and_stochastic(B, O, C):
+    """Every instantiation of the pair-table kernel (1..16 cells: full groups, ragged tail groups, the
+    three-block register budgets), deterministic and with Philox noise, with the fused auto-reset."""
+    n = 3001
+    for stochastic in (False, True):
+        S = 4 if C % 2 else 3
+        difficulty = "hard" if (C >= 3 and C % 3) else "easy"
+        env = B.CellularVectorEnv(num_envs=n, n_cells=C, n_states=S, stochastic=stochastic, env_seed=C, max_episode_steps=5,
+                                  difficulty=difficulty)
+        ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, noise=stochastic, rng_episodic=True, seed=C, max_episode_steps=5,
+                          difficulty=difficulty, reward="nonlinear_rp" if stochastic else "right_polarizing")
+        _rollout(env, ora, 8, np.random.default_rng(100 + C), check_every=4)
+
+
 @pytest.mark.parametrize("C,S,stochastic", [(3, 3, True), (2, 3, False), (16, 4, True), (16, 4, False), (1, 4, True)])
 def test_generic_kernel_equals_oracle(B, O, C, S, stochastic):
     """The generic per-cell kernel (used for 5-8 levels or per-cell side-effect tables) on shapes the
