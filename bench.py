@@ -409,18 +409,23 @@ def ncu_traffic(workload):
     return None
 
 
-def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps):
+def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps, side=True):
+    """`side` = also time the CUDA-graph and fused-rollout variants (single process only)."""
     import torch
     batches = build_batches(workload, device, rank)
     n_rank = sum(b["n"] for b in batches)
     ms, launches, clocks = time_device_path(batches, steps, warmup, dist, device, device.index)
+    if not side:
+        dist_for_side = True          # any non-None value skips the two side measurements below
+    else:
+        dist_for_side = dist
     graph_res = None
-    if WORKLOADS[workload]["l2_resident"] and dist is None:
+    if WORKLOADS[workload]["l2_resident"] and dist_for_side is None:
         g_ms, g_steps = time_graph_path(batches, steps, device)
         graph_res = {"value": n_rank * g_steps / (g_ms * 1e-3), "ms_per_step": g_ms / g_steps,
                      "steps_per_graph": RING}
     ro_res = None
-    if dist is None:                       # K-step fused rollout (random actions generated in the kernel)
+    if dist_for_side is None:              # K-step fused rollout (random actions generated in the kernel)
         K = 64
         main = torch.cuda.current_stream(device)
         ro_streams = [main] if len(batches) == 1 else [torch.cuda.Stream(device=device) for _ in batches]
@@ -486,6 +491,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg2/cfg3/cfg5 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true",
+                    help="skip the CUDA-graph and fused-rollout side measurements (profiling runs: launch lists)")
     ap.add_argument("--host-chunk", type=int, default=None, help="envs per chunk of the host (e2e) path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -521,7 +528,8 @@ def main():
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     e2e_steps = max(3, min(args.steps, 10))
-    main_res = bench_workload(args.workload, args.steps, args.warmup, dist, device, world, rank, e2e_steps)
+    main_res = bench_workload(args.workload, args.steps, args.warmup, dist, device, world, rank, e2e_steps,
+                              side=not args.no_side)
     extra = {}
     if world == 1 and not args.no_extra:
         for w in ("cfg2", "cfg3", "cfg5"):

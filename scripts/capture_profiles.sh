@@ -1,7 +1,7 @@
 # Capture recipe for profiles/: plain runs first, then ncu launch lists and --set full reports.
 mkdir -p gpurun_out
 set -x
-B="python bench.py --steps 20 --warmup 3 --no-extra --no-cpu-baseline"
+B="python bench.py --steps 20 --warmup 3 --no-extra --no-cpu-baseline --no-side"
 $B > gpurun_out/plain.log 2>&1 || exit 1
 $B --workload cfg5 > gpurun_out/plain5.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_cfg4.csv $B > gpurun_out/ncu1.log 2>&1
