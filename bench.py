@@ -9,8 +9,10 @@ A "step" is one pass of the hot path (env.step for every env of the batch) over 
 synthetic random actions.  Rank 0 prints ONE JSON line (contract in the task statement):
   value      whole-job env-steps/s with actions already resident in HBM (device path, one kernel
              launch per step per GPU), timed with CUDA events, max over ranks
-  e2e        the same metric through the host-facing call (numpy in, numpy out: gc_step_host does
-             H2D of the actions, the kernel and D2H of observation/reward/index/flags every step)
+  e2e        the same metric through the host-facing call (numpy in, numpy out, H2D + kernel + D2H every
+             step).  Cellular workloads use the packed wire format (gc_step_host_packed: one action word in,
+             state word + reward + flag byte out per env); grid world the int8 one (gc_step_host)
+  packed     device path of the packed layout (25 B per env-step instead of 3C + 20), with its own roofline
   roofline   algorithmic HBM bytes per launch / measured launch time, against MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle port (oracle/gc_oracle.c) on all host cores, bounded sample
 
@@ -20,7 +22,8 @@ Workloads (BASELINE.json configs; per-GPU batch fixed => weak scaling):
   cfg2            default polarisation env (3 cells x 3 levels), 65,536 envs (1.9 MB: L2-resident)
   cfg3            grid world, 2^20 envs, stochastic dispersal + fused auto-reset (27 MB: L2-resident)
   cfg5            mixed: per GPU 4M stochastic polarisation + 4M grid world envs (64M at 8 GPUs)
-The default line also carries cfg2/cfg3/cfg5 results under "workloads" when run on 1 GPU.
+The default line also carries cfg2/cfg3/cfg5 results under "workloads" on 1 GPU, and cfg5 (the multi-GPU
+config of BASELINE.json) at every N > 1, where the line also holds a shard check run on the hardware.
 """
 import argparse
 import json
@@ -134,18 +137,24 @@ class ClockSampler:
 HOST_CHUNK_ENVS = 1 << 20
 
 
-def build_batches(workload, device, rank, n_override=None, env_scale=1.0):
-    """Creates the vector envs of one rank and their pre-generated device action rings."""
+STATS_EVERY = 64     # steps per "iteration": the episode statistics are all-reduced once per iteration
+
+
+def build_batches(workload, device, rank, n_override=None, packed=False):
+    """Creates the vector envs of one rank and their pre-generated device action rings.  `packed`: the
+    cellular sub-batches use the packed-word layout (PackedCellularVectorEnv)."""
     import torch
-    from gym_cellular_b200 import CellularVectorEnv
+    from gym_cellular_b200 import CellularVectorEnv, PackedCellularVectorEnv
     w = WORKLOADS[workload]
     n_total = int(n_override or w["n_envs"])
     batches, offset = [], rank * n_total
     gen = torch.Generator(device=device).manual_seed(1234 + rank)
     for kind, frac, kw in w["parts"]:
         n = int(n_total * frac) // 16 * 16
-        env = CellularVectorEnv(kind=kind, num_envs=n, device=device, env_seed=0, env_id_offset=offset,
-                                emit_side_effects=False, collect_stats=True, host_chunk_envs=HOST_CHUNK_ENVS, **kw)
+        use_packed = packed and kind == "cellular"
+        cls = PackedCellularVectorEnv if use_packed else CellularVectorEnv
+        env = cls(kind=kind, num_envs=n, device=device, env_seed=0, env_id_offset=offset,
+                  emit_side_effects=False, collect_stats=True, host_chunk_envs=HOST_CHUNK_ENVS, **kw)
         offset += n
         ring = []
         for _ in range(RING):
@@ -158,32 +167,53 @@ def build_batches(workload, device, rank, n_override=None, env_scale=1.0):
                 a[1] = torch.where(jur == 1, pos, a[1])
             else:
                 a = torch.randint(0, env.n_actions, (env.n_cells, env.ld), dtype=torch.int8, device=device, generator=gen)
+            if use_packed:                  # the same actions as packed words (2 bits per cell)
+                w32 = torch.zeros(env.ld, dtype=torch.int32, device=device)
+                w32[:n] = env.pack(a[:, :n])
+                a = w32
             ring.append(a)
-        batches.append(dict(env=env, ring=ring, kind=kind, n=n, bytes=bytes_per_env_step(kind, env.n_cells)))
+        batches.append(dict(env=env, ring=ring, kind=kind, n=n, packed=use_packed,
+                            bytes=env.hbm_bytes_per_env_step if use_packed else bytes_per_env_step(kind, env.n_cells)))
     return batches
 
 
 
-def time_device_path(batches, steps, warmup, dist, device, sampler_index):
-    """Device path.  Independent sub-batches (the mixed config 5) step on one stream each, so that
-    the tail of one kernel overlaps the head of the other; everything is bracketed by events on the
-    main stream, which the side streams are ordered against."""
+def time_device_path(batches, steps, warmup, dist, device, sampler_index, reducer=None):
+    """Device path.  Every step of a sub-batch is one kernel launch on the sub-batch's own stream
+    (independent sub-batches -- the mixed config 5 -- overlap tail and head); the launches are issued by
+    gc_step_many, STATS_EVERY steps per foreign call, chained by programmatic dependent launch.  After
+    every STATS_EVERY steps (one "iteration") the episode statistics are all-reduced over the ranks (NCCL,
+    asynchronously on a side stream) -- INSIDE the timed region, which ends when the last reduction has."""
     import torch
     main = torch.cuda.current_stream(device)
     streams = [main] if len(batches) == 1 else [torch.cuda.Stream(device=device) for _ in batches]
-    # one device-path step = one pre-bound ctypes call = one kernel, on the sub-batch's own stream
-    calls = [[b["env"].bind_step(a, stream=s) for a in b["ring"]] for b, s in zip(batches, streams)]
+    slots = [[b["env"]._bind(a) for a in b["ring"]] for b in batches]
 
     def run(lo, hi):
         for s in streams:
             if s is not main:
                 s.wait_stream(main)
-        for i in range(lo, hi):
-            for c in calls:
-                c[i % RING]()
+        pending = None
+        for c0 in range(lo, hi, STATS_EVERY):
+            c1 = min(hi, c0 + STATS_EVERY)
+            for b, sl, s in zip(batches, slots, streams):
+                order = [sl[i % RING] for i in range(c0, min(c1, c0 + RING))]
+                b["env"].step_many(order, c1 - c0, stream=s)
+            if reducer is not None:
+                for s in streams:
+                    if s is not main:
+                        main.wait_stream(s)
+                if pending is not None:
+                    pending.wait()
+                pending = reducer.start(sum_stats(batches))
+                for s in streams:
+                    if s is not main:
+                        s.wait_stream(main)
         for s in streams:
             if s is not main:
                 main.wait_stream(s)
+        if pending is not None:
+            pending.wait()
 
     run(0, warmup)
     torch.cuda.synchronize(device)
@@ -192,9 +222,12 @@ def time_device_path(batches, steps, warmup, dist, device, sampler_index):
     torch.cuda.synchronize(device)
     launches0 = sum(b["env"].launch_count for b in batches)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host = 0.0
     with ClockSampler(sampler_index) as clk:
         start.record(main)
+        t0 = time.perf_counter()
         run(warmup, warmup + steps)
+        t_host = time.perf_counter() - t0
         stop.record(main)
         stop.synchronize()
     ms = start.elapsed_time(stop)
@@ -205,7 +238,12 @@ def time_device_path(batches, steps, warmup, dist, device, sampler_index):
         ms = float(t.item())
         dist.barrier()
     torch.cuda.synchronize(device)
-    return ms, launches, clk.summary()
+    return ms, launches, clk.summary(), 1e6 * t_host / max(launches, 1)
+
+
+def sum_stats(batches):
+    import torch
+    return torch.stack([b["env"]._stats for b in batches]).sum(0)
 
 
 def time_graph_path(batches, steps, device):
@@ -226,21 +264,40 @@ def time_graph_path(batches, steps, device):
     return start.elapsed_time(stop), reps * RING
 
 
-def measure_pcie(device, nbytes=1 << 28):
-    """Pinned-memory copy bandwidth of this box (GB/s), for reading the e2e figure: the host path
-    moves (C) bytes in and (C + 12) bytes out per env-step and is bound by these two numbers."""
+def measure_pcie(device, dist=None, nbytes=1 << 27):
+    """Pinned-memory copy bandwidth of this box (GB/s per GPU): each direction alone and both at once --
+    the ceiling of the e2e figure, which moves h2d + d2h bytes per step.  With several ranks all of them
+    measure at the same time (barrier first), so the figure is the per-GPU share of the host's aggregate."""
     import torch
-    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    d = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    out = {}
-    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
-        dst.copy_(src, non_blocking=True)
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def run(h2d, d2h, reps=4):
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
-        for _ in range(3):
-            dst.copy_(src, non_blocking=True)
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
         torch.cuda.synchronize(device)
-        out[name] = round(3 * nbytes / (time.perf_counter() - t0) / 1e9, 1)
+        return reps * nbytes / (time.perf_counter() - t0) / 1e9
+    run(True, True, 1)
+    out = {"h2d_gbs": round(run(True, False), 1), "d2h_gbs": round(run(False, True), 1)}
+    out["duplex_gbs_each"] = round(run(True, True), 1)
+    if dist is not None:
+        t = torch.tensor([out["h2d_gbs"], out["d2h_gbs"], out["duplex_gbs_each"]], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        out["all_ranks_concurrent_sum"] = {"h2d_gbs": round(float(t[0]), 1), "d2h_gbs": round(float(t[1]), 1),
+                                           "duplex_gbs_each": round(float(t[2]), 1)}
     return out
 
 
@@ -250,14 +307,14 @@ def time_host_path(batches, steps, warmup, dist, device):
     host_rings = []
     for b in batches:
         ring = [b["ring"][i].cpu().pin_memory() for i in range(2)]
-        host_rings.append([(t, t.numpy()) for t in ring])
+        host_rings.append([(t, t.numpy()[:b["n"]] if b["packed"] else t.numpy()[:, :b["n"]]) for t in ring])
     h2d = sum(b["env"].host_bytes_per_env_step[0] * b["n"] for b in batches)
     d2h = sum(b["env"].host_bytes_per_env_step[1] * b["n"] for b in batches)
 
     def one(i):
         sink = 0.0
         for b, hr in zip(batches, host_rings):
-            obs, rew, term, trunc, info = b["env"].step(hr[i % 2][1][:, :b["n"]])
+            obs, rew, term, trunc, info = b["env"].step(hr[i % 2][1])
             sink += float(rew[0])
         return sink
     for i in range(warmup):
@@ -300,8 +357,7 @@ def oracle_envs(workload, n_sample):
     return out
 
 
-def time_oracle(workload, n_sample, steps, warmup, threads):
-    envs = oracle_envs(workload, n_sample)
+def time_oracle(envs, steps, warmup, threads):
     for _ in range(warmup):
         for env, a, n in envs:
             env.step_parallel(a, threads)
@@ -310,7 +366,27 @@ def time_oracle(workload, n_sample, steps, warmup, threads):
         for env, a, n in envs:
             env.step_parallel(a, threads)
     el = time.perf_counter() - t0
-    return sum(n for _, _, n in envs) * steps / el, el, sum(n for _, _, n in envs)
+    return sum(n for _, _, n in envs) * steps / el, el
+
+
+ORACLE_REPS = 3
+
+
+def oracle_rate(workload, steps, warmup, budget_s):
+    """The C oracle port on all host cores, the same sampling for the cpu_baseline leg and the reference
+    arm: a calibration pass sizes the sample so that one repetition of (warmup + steps) steps takes about
+    budget_s / ORACLE_REPS seconds; ORACLE_REPS repetitions, the MEDIAN rate is reported (the spread between
+    repetitions on one box was 40 % in round 1: thread placement / first touch)."""
+    threads = os.cpu_count() or 1
+    rate, _ = time_oracle(oracle_envs(workload, 1 << 16), 2, 1, threads)          # calibration
+    per_rep = budget_s / ORACLE_REPS
+    n_sample = int(min(1 << 22, max(1 << 12, rate * per_rep / max(steps + warmup, 1))))
+    envs = oracle_envs(workload, n_sample)
+    reps = sorted(time_oracle(envs, steps, warmup if i == 0 else 0, threads) for i in range(ORACLE_REPS))
+    rate, el = reps[len(reps) // 2]
+    n = sum(n for _, _, n in envs)
+    return {"rate": rate, "seconds": el, "envs": n, "threads": threads, "steps": steps,
+            "reps": [round(r) for r, _ in reps]}
 
 
 def python_port_rate(workload):
@@ -328,36 +404,134 @@ def python_port_rate(workload):
         return {"error": type(exc).__name__}
 
 
-def cpu_baseline(workload, budget_s=12.0):
-    threads = os.cpu_count() or 1
-    rate, _, _ = time_oracle(workload, 1 << 16, 2, 1, threads)          # calibration
-    n_sample = int(min(1 << 22, max(1 << 14, rate * budget_s / 8)))
-    steps = 24
-    rate, el, n = time_oracle(workload, n_sample, steps, 1, threads)
-    return {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": f"C oracle (oracle/gc_oracle.c), {n} envs x {steps} steps of {workload}, {threads} threads, "
-                      f"{el:.1f} s wall = {el * threads:.0f} core-seconds",
-            "python_port": python_port_rate(workload)}
+def _pyport_env_fn(n_cells, n_levels):
+    """env_fn for the AsyncVectorEnv baseline: the pure-Python port of the reference step with the reference's
+    spaces attached (cells3states3actions3.py:65-89)."""
+    def make():
+        from gym_cellular_b200._gym import gym
+        from oracle.pyport import PolarisationEnv
+        env = PolarisationEnv(n_cells, n_levels)
+        sp = gym.spaces
+        env.observation_space = sp.Tuple([sp.Discrete(n_levels) for _ in range(n_cells)])
+        env.action_space = sp.Tuple([sp.Discrete(n_levels) for _ in range(n_cells)])
+        return env
+    return make
+
+
+def async_vector_env_rate(n_cells, n_levels, envs_per_worker, steps):
+    """The CPU baseline BASELINE.json names: the reference's step loop (its pure-Python port -- the reference
+    itself cannot travel to the GPU box) under gymnasium.vector.AsyncVectorEnv (the multiprocessing
+    stand-in of gym_cellular_b200/compat when gymnasium is absent): one worker per core, one pipe round trip
+    per step, num_envs = workers x envs_per_worker."""
+    import numpy as np
+    from gym_cellular_b200._gym import gym
+    workers = os.cpu_count() or 1
+    n = workers * envs_per_worker
+    fns = [_pyport_env_fn(n_cells, n_levels) for _ in range(n)]
+    try:
+        env = gym.vector.AsyncVectorEnv(fns, shared_memory=False, envs_per_worker=envs_per_worker)
+        layout = f"{workers} workers x {envs_per_worker} envs"
+    except TypeError:                      # real gymnasium: one process per env
+        n = workers
+        env = gym.vector.AsyncVectorEnv(fns[:n], shared_memory=False)
+        layout = f"{workers} workers x 1 env"
+    try:
+        env.reset()
+        rng = np.random.default_rng(0)
+        acts = [tuple(rng.integers(0, n_levels, n) for _ in range(n_cells)) for _ in range(8)]
+        for i in range(3):
+            env.step(acts[i % 8])
+        t0 = time.perf_counter()
+        for i in range(steps):
+            env.step(acts[i % 8])
+        el = time.perf_counter() - t0
+    finally:
+        env.close()
+    return {"value": n * steps / el, "unit": "env-steps/s", "layout": layout, "steps": steps,
+            "shape": f"{n_cells} cells x {n_levels} levels", "harness": gym.vector.AsyncVectorEnv.__module__}
+
+
+def config1_rates():
+    """BASELINE config 1: Cells3States3Actions3-v0, ONE env, 10 000 random-action steps.  The reference's
+    Python cannot travel to the GPU box; its pure-Python port is timed in-process (the reference itself:
+    2.4e5 steps/s on one core).  Also the drop-in single-env class of this package through
+    gymnasium.make, whose step() is one N = 1 kernel launch plus a device-to-host read."""
+    import numpy as np
+    from oracle.pyport import PolarisationEnv
+    out = {}
+    rng = np.random.default_rng(0)
+    acts = [tuple(int(x) for x in rng.integers(0, 3, 3)) for _ in range(10000)]
+    env = PolarisationEnv(3, 3)
+    env.reset()
+    t0 = time.perf_counter()
+    for a in acts:
+        env.step(a)
+    out["python_port_one_env"] = {"value": len(acts) / (time.perf_counter() - t0), "unit": "env-steps/s", "steps": len(acts)}
+    try:
+        import gym_cellular_b200  # noqa: F401
+        from gym_cellular_b200._gym import gym
+        env = gym.make("gym_cellular/Cells3States3Actions3-v0")
+        env.reset()
+        for a in acts[:50]:
+            env.step(a)
+        t0 = time.perf_counter()
+        for a in acts[:2000]:
+            env.step(a)
+        out["native_single_env_drop_in"] = {"value": 2000 / (time.perf_counter() - t0), "unit": "env-steps/s", "steps": 2000,
+                                            "note": "gymnasium.make id, one N=1 kernel launch + D2H per step"}
+        env.close()
+    except Exception as exc:            # pragma: no cover
+        out["native_single_env_drop_in"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
+def cpu_baseline(workload, budget_s=18.0):
+    r = oracle_rate(workload, 8, 1, budget_s)
+    out = {"value": r["rate"], "unit": "env-steps/s", "cores": r["threads"], "kind": "port",
+           "sample": f"C oracle (oracle/gc_oracle.c), {r['envs']} envs x {r['steps']} steps of {workload}, {r['threads']} threads, "
+                     f"median of {ORACLE_REPS} repetitions {r['reps']} ({r['seconds']:.1f} s each)",
+           "python_port": python_port_rate(workload)}
+    part = next((kw for kind, _, kw in WORKLOADS[workload]["parts"] if kind == "cellular"), None)
+    try:
+        out["async_vector_env"] = {"config1_shape": async_vector_env_rate(3, 3, 64, 60)}
+        if part is not None and (part["n_cells"], part["n_states"]) != (3, 3):
+            out["async_vector_env"]["bench_shape"] = async_vector_env_rate(part["n_cells"], part["n_states"], 16, 30)
+    except Exception as exc:            # pragma: no cover - depends on the box
+        out["async_vector_env"] = {"error": f"{type(exc).__name__}: {exc}"}
+    out["config1"] = config1_rates()
+    return out
+
+
+def workload_config(workload, world):
+    """The `config` object of the JSON line: a function of the workload and the world size only, so that
+    the native and the reference arm print the same one."""
+    w = WORKLOADS[workload]
+    return {"workload": workload, "description": w["desc"], "envs_per_gpu": w["n_envs"] // 16 * 16,
+            "global_envs": w["n_envs"] // 16 * 16 * world,
+            "parallelism": f"env-sharded x{world}, NCCL all-reduce of episode statistics once per iteration "
+                           f"({STATS_EVERY} steps), inside the timed region",
+            "l2": "per-step working set larger than L2" if not w["l2_resident"]
+                  else "working set is L2-resident (launch-bound, not an HBM measurement)",
+            "actions": f"ring of {RING} pre-generated buffers, uniform random"}
 
 
 def run_reference_arm(args, workload):
     """--impl reference: the CPU implementation on the host cores (the reference is pure Python and
-    cannot travel to the GPU box; the oracle port stands in)."""
+    cannot travel to the GPU box; the oracle port stands in).  Each step is a bounded sample
+    of the workload (cpu_baseline.sample says how many envs); same sampling as the native arm's
+    cpu_baseline leg."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    rate, _, _ = time_oracle(workload, 1 << 16, 2, 1, threads)
-    total = args.steps + args.warmup
-    n_sample = int(min(1 << 22, max(1 << 12, rate * 60.0 / max(total, 1))))
-    rate, el, n = time_oracle(workload, n_sample, args.steps, args.warmup, threads)
-    sample = f"C oracle (oracle/gc_oracle.c), {n} envs per step of {workload}, {threads} threads"
-    line = {"impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/f64", "data": "synthetic",
-            "config": {"workload": workload, "description": WORKLOADS[workload]["desc"], "sample_envs": n},
-            "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    r = oracle_rate(workload, args.steps, args.warmup, 60.0)
+    sample = (f"C oracle (oracle/gc_oracle.c), {r['envs']} envs per step of {workload}, {r['threads']} threads, "
+              f"median of {ORACLE_REPS} repetitions {r['reps']}")
+    line = {"impl": "reference", "metric": "env-steps/sec", "value": r["rate"], "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/int32 state, f32 reward",
+            "data": "synthetic", "config": workload_config(workload, args.gpus),
+            "cpu_baseline": {"value": r["rate"], "unit": "env-steps/s", "cores": r["threads"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["rate"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -399,7 +573,7 @@ def measured_peak():
 
 
 def ncu_traffic(workload):
-    """dram read+write bytes per launch from the committed ncu capture, if any (profiles/traffic.json)."""
+    """dram read+write bytes per step from the committed ncu capture, if any (profiles/traffic.json)."""
     path = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
@@ -409,23 +583,38 @@ def ncu_traffic(workload):
     return None
 
 
+def roofline_of(workload, batches, step_s, tag=None):
+    alg_bytes = sum(b["bytes"] * b["n"] for b in batches)           # per step, per rank
+    n_rank = sum(b["n"] for b in batches)
+    peak, peak_src = measured_peak()
+    traffic = ncu_traffic(tag or workload)
+    static = WORKLOADS[workload]["l2_resident"]
+    # part of a working set that fits the 126 MB L2 never reaches DRAM: say so from the measured traffic
+    dram_share = None if not isinstance(traffic, (int, float)) else traffic / alg_bytes
+    return {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": alg_bytes / step_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes // len(batches), "bytes_per_env_step": alg_bytes / n_rank,
+            "kernels_per_step": len(batches),
+            "dram_bytes_over_algorithmic": None if dram_share is None else round(dram_share, 3),
+            "l2_resident": static if dram_share is None else ("partly" if 0.25 <= dram_share < 0.75 else dram_share < 0.25)}
+
+
 def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps, side=True):
     """`side` = also time the CUDA-graph and fused-rollout variants (single process only)."""
     import torch
+    from gym_cellular_b200.distributed import StatsReducer
     batches = build_batches(workload, device, rank)
     n_rank = sum(b["n"] for b in batches)
-    ms, launches, clocks = time_device_path(batches, steps, warmup, dist, device, device.index)
-    if not side:
-        dist_for_side = True          # any non-None value skips the two side measurements below
-    else:
-        dist_for_side = dist
+    reducer = StatsReducer()
+    ms, launches, clocks, host_us = time_device_path(batches, steps, warmup, dist, device, device.index, reducer)
+    single = dist is None and side
     graph_res = None
-    if WORKLOADS[workload]["l2_resident"] and dist_for_side is None:
+    if WORKLOADS[workload]["l2_resident"] and single:
         g_ms, g_steps = time_graph_path(batches, steps, device)
         graph_res = {"value": n_rank * g_steps / (g_ms * 1e-3), "ms_per_step": g_ms / g_steps,
                      "steps_per_graph": RING}
     ro_res = None
-    if dist_for_side is None:              # K-step fused rollout (random actions generated in the kernel)
+    if single:              # K-step fused rollout (random actions generated in the kernel)
         K = 64
         main = torch.cuda.current_stream(device)
         ro_streams = [main] if len(batches) == 1 else [torch.cuda.Stream(device=device) for _ in batches]
@@ -451,27 +640,20 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
         r1.synchronize()
         ro_res = {"value": n_rank * K * reps / (r0.elapsed_time(r1) * 1e-3), "steps_per_launch": K,
                   "note": "fused rollout: state in registers, actions generated in-kernel (not per-step step())"}
-    el_host, h2d, d2h = time_host_path(batches, e2e_steps, 2, dist, device)
-    # the only collective of the path: episode statistics, all-reduced once per iteration (NCCL, side stream)
-    from gym_cellular_b200.distributed import StatsReducer
-    totals = StatsReducer().start(torch.stack([b["env"]._stats for b in batches]).sum(0)).result()
-    alg_bytes = sum(b["bytes"] * b["n"] for b in batches)           # per step, per rank
-    peak, peak_src = measured_peak()
+    # episode statistics over all ranks: the path's only collective; totals must add up exactly
+    totals = reducer.start(sum_stats(batches)).result()
+    expect = world * n_rank * (steps + warmup + (g_steps + RING if graph_res else 0) + (K * (reps + 1) if ro_res else 0))
+    stats_ok = totals["env_steps"] == expect
     step_s = ms * 1e-3 / steps
     res = {
         "value": world * n_rank * steps / (ms * 1e-3),
         "ms_per_step": ms / steps,
         "envs_per_gpu": n_rank,
         "gpu_launches": launches * world,
+        "host_us_per_launch": round(host_us, 2),
         "clocks": clocks,
-        "e2e": {"value": world * n_rank * e2e_steps / el_host, "unit": "env-steps/s",
-                "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps},
-        "roofline": {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg_bytes / step_s / 1e9 / peak, "traffic": ncu_traffic(workload),
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes // len(batches),
-                     "bytes_per_env_step": alg_bytes / n_rank, "kernels_per_step": len(batches),
-                     "l2_resident": WORKLOADS[workload]["l2_resident"]},
-        "episode_stats": totals,
+        "roofline": roofline_of(workload, batches, step_s),
+        "episode_stats": dict(totals, env_steps_expected=expect, consistent=stats_ok),
         "cuda_graph": graph_res,
         "fused_rollout": ro_res,
     }
@@ -479,7 +661,71 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
         b["env"].close()
     del batches
     torch.cuda.empty_cache()
+
+    # ---- packed layout: device path (cellular sub-batches as packed words) and the e2e host path ---------
+    has_cell = any(kind == "cellular" for kind, _, _ in WORKLOADS[workload]["parts"])
+    pbatches = build_batches(workload, device, rank, packed=True)
+    if has_cell:
+        p_ms, p_launches, _, p_host_us = time_device_path(pbatches, steps, warmup, dist, device, device.index, reducer)
+        res["packed"] = {"value": world * n_rank * steps / (p_ms * 1e-3), "ms_per_step": p_ms / steps,
+                         "gpu_launches": p_launches * world, "host_us_per_launch": round(p_host_us, 2),
+                         "layout": "cellular sub-batches: one 32-bit word per env for the state, one for the action "
+                                   "(2 bits per cell), reward + one flag byte out",
+                         "roofline": roofline_of(workload, pbatches, p_ms * 1e-3 / steps, tag=workload + "_packed")}
+    el_host, h2d, d2h = time_host_path(pbatches, e2e_steps, 2, dist, device)
+    res["e2e"] = {"value": world * n_rank * e2e_steps / el_host, "unit": "env-steps/s",
+                  "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                  "ms_per_step": 1e3 * el_host / e2e_steps,
+                  "wire": "packed words for the cellular sub-batches (4 B in, 9 B out per env-step; state word = "
+                          "tabular index at 4 levels), int8 layout for grid world (2 B in, 13 B out); the constant "
+                          "`terminated` flag is not copied",
+                  "link_gbs_per_gpu": {"h2d": h2d / el_host * e2e_steps / 1e9, "d2h": d2h / el_host * e2e_steps / 1e9}}
+    for b in pbatches:
+        b["env"].close()
+    del pbatches
+    torch.cuda.empty_cache()
     return res
+
+
+def shard_check(dist, device, rank, world):
+    """On the hardware, over NCCL: rank r re-steps the first 65,536 envs of rank (r+1) % N's shard of the
+    mixed config (stochastic polarisation + grid world, Philox keyed by GLOBAL env id) on its own GPU and
+    the CRCs are compared with the owner's -- results must not depend on which GPU owns an env."""
+    import zlib
+    import torch
+    from gym_cellular_b200 import CellularVectorEnv
+    n, T = 1 << 16, 6
+    n_total = WORKLOADS["cfg5"]["n_envs"]
+
+    def crc_of(owner):
+        gen = torch.Generator(device=device).manual_seed(777 + owner)
+        offset, h = owner * n_total, 0
+        for kind, frac, kw in WORKLOADS["cfg5"]["parts"]:
+            env = CellularVectorEnv(kind=kind, num_envs=n, device=device, env_seed=0, env_id_offset=offset,
+                                    emit_side_effects=False, **kw)
+            offset += int(n_total * frac) // 16 * 16
+            for _ in range(T):
+                if kind == "gridworld":
+                    a = torch.full((2, n), 4, dtype=torch.int8, device=device)
+                    jur = torch.randint(0, 2, (n,), device=device, generator=gen)
+                    pos = torch.randint(0, 4, (n,), device=device, generator=gen).to(torch.int8)
+                    a[0] = torch.where(jur == 0, pos, a[0])
+                    a[1] = torch.where(jur == 1, pos, a[1])
+                else:
+                    a = torch.randint(0, env.n_actions, (env.n_cells, n), dtype=torch.int8, device=device, generator=gen)
+                env.step_device(a)
+                for t in (env.state, env._index[:n], env._reward[:n], env._unsafe[:n], env._count[:n]):
+                    h = zlib.crc32(t.cpu().numpy().tobytes(), h)
+            env.close()
+        return h
+    mine, neighbour = crc_of(rank), crc_of((rank + 1) % world)
+    t = torch.tensor([mine, neighbour], dtype=torch.int64, device=device)
+    allv = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allv, t)
+    ok = all(int(allv[r][1]) == int(allv[(r + 1) % world][0]) for r in range(world))
+    distinct = len({int(v[0]) for v in allv}) == world            # different shards really differ
+    return {"result": "ok" if (ok and distinct) else "MISMATCH", "envs_per_rank_checked": 2 * n, "steps": T,
+            "what": "rank r re-steps the head of rank (r+1)%N's shard (env_id_offset); CRC32 of state/index/reward/flags all-gathered"}
 
 
 def main():
@@ -530,33 +776,53 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     main_res = bench_workload(args.workload, args.steps, args.warmup, dist, device, world, rank, e2e_steps,
                               side=not args.no_side)
+    # side workloads: the launch-bound configs 2 and 3 on one GPU (with enough steps that a short driver run is
+    # not a pipeline-fill measurement), the mixed multi-GPU config 5 at every N
     extra = {}
-    if world == 1 and not args.no_extra:
-        for w in ("cfg2", "cfg3", "cfg5"):
+    side_steps = max(args.steps, 500)
+    if not args.no_extra:
+        for w in (("cfg2", "cfg3", "cfg5") if world == 1 else ("cfg5",)):
             if w != args.workload:
-                r = bench_workload(w, args.steps, args.warmup, None, device, 1, 0, e2e_steps)
+                r = bench_workload(w, side_steps, args.warmup, dist, device, world, rank, e2e_steps, side=not args.no_side)
                 extra[w] = {"description": WORKLOADS[w]["desc"], "value": r["value"], "ms_per_step": r["ms_per_step"],
+                            "steps": side_steps, "host_us_per_launch": r["host_us_per_launch"],
                             "roofline_frac": r["roofline"]["frac"], "achieved_gbs": r["roofline"]["achieved"],
-                            "l2_resident": WORKLOADS[w]["l2_resident"], "e2e": r["e2e"]["value"],
-                            "kernels_per_step": r["roofline"]["kernels_per_step"], "cuda_graph": r["cuda_graph"], "fused_rollout": r["fused_rollout"]}
+                            "traffic": r["roofline"]["traffic"],
+                            "dram_bytes_over_algorithmic": r["roofline"]["dram_bytes_over_algorithmic"],
+                            "l2_resident": r["roofline"]["l2_resident"], "e2e": r["e2e"]["value"],
+                            "e2e_bytes_per_step": [r["e2e"]["h2d_bytes_per_step"], r["e2e"]["d2h_bytes_per_step"]],
+                            "kernels_per_step": r["roofline"]["kernels_per_step"], "cuda_graph": r["cuda_graph"],
+                            "fused_rollout": r["fused_rollout"], "episode_stats_consistent": r["episode_stats"]["consistent"],
+                            "packed": None if "packed" not in r else
+                            {k: r["packed"][k] for k in ("value", "ms_per_step")} | {"roofline_frac": r["packed"]["roofline"]["frac"],
+                                                                                    "bytes_per_env_step": r["packed"]["roofline"]["bytes_per_env_step"]}}
+    pcie = measure_pcie(device, dist)
+    check = shard_check(dist, device, rank, world) if dist is not None else None
     if rank == 0:
+        link = pcie.get("duplex_gbs_each")
+        e2e = dict(main_res["e2e"], pcie_measured=pcie)
+        if link:
+            # the host path is bound by the busier direction of the link while both directions are in use
+            need = max(e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]) / world
+            e2e["link_ceiling_env_steps_per_s"] = world * main_res["envs_per_gpu"] / (need / (link * 1e9))
+            e2e["frac_of_link_ceiling"] = e2e["value"] / e2e["link_ceiling_env_steps_per_s"]
         line = {
             "metric": "env-steps/sec", "value": main_res["value"], "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/int32 state, f32 reward",
             "data": "synthetic",
-            "config": {"workload": args.workload, "description": WORKLOADS[args.workload]["desc"],
-                       "envs_per_gpu": main_res["envs_per_gpu"], "global_envs": main_res["envs_per_gpu"] * world,
-                       "parallelism": f"env-sharded x{world}, NCCL all-reduce of episode statistics once per iteration",
-                       "l2": "per-step working set larger than L2" if not WORKLOADS[args.workload]["l2_resident"]
-                             else "working set is L2-resident (launch-bound, not an HBM measurement)",
-                       "actions": f"ring of {RING} pre-generated device buffers, uniform random",
-                       "host_affinity": affinity},
-            "e2e": {**main_res["e2e"], "pcie_measured": measure_pcie(device)},
-            "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
-            "roofline": main_res["roofline"], "episode_stats": main_res["episode_stats"],
+            "config": workload_config(args.workload, world),
+            "host_affinity": affinity,
+            "e2e": e2e,
+            "gpu_launches": main_res["gpu_launches"], "host_us_per_launch": main_res["host_us_per_launch"],
+            "clocks": main_res["clocks"],
+            "roofline": main_res["roofline"], "packed": main_res.get("packed"),
+            "episode_stats": main_res["episode_stats"],
             "fused_rollout": main_res["fused_rollout"], "cuda_graph": main_res["cuda_graph"],
         }
+        if check is not None:
+            line["shard_check"] = check["result"]
+            line["shard_check_detail"] = check
         if extra:
             line["workloads"] = extra
         if world == 1 and not args.no_cpu_baseline:

@@ -7,6 +7,7 @@ from ._gym import gym  # noqa: F401  (real gymnasium, or the structural stand-in
 from . import tables
 from .tables import right_polarizing, multiple_optima, nonlinear, nonlinear_right_polarizing
 from .vector_env import CellularVectorEnv, make_vector_env
+from .packed_env import PackedCellularVectorEnv
 from .codec import (generalized_cellular2tabular, generalized_tabular2cellular, cellular2tabular,
                     tabular2cellular)
 from .envs import (Cells3States3Actions3Env, Cells2Rest3Env, Cells3ResetVDeadlockEnv, GridWorldEnv,
@@ -15,7 +16,7 @@ from .envs import (Cells3States3Actions3Env, Cells2Rest3Env, Cells3ResetVDeadloc
 from . import registration  # noqa: F401  (registers the gym_cellular/<Name>-v0 ids)
 from .alias import install_alias
 
-__all__ = ["CellularVectorEnv", "make_vector_env", "tables", "right_polarizing", "multiple_optima",
+__all__ = ["CellularVectorEnv", "PackedCellularVectorEnv", "make_vector_env", "tables", "right_polarizing", "multiple_optima",
            "nonlinear", "nonlinear_right_polarizing", "Cells3States3Actions3Env", "Cells2Rest3Env",
            "Cells3ResetVDeadlockEnv", "GridWorldEnv", "PriorKnowledge", "GridWorldPriorKnowledge",
            "generalized_cellular2tabular", "generalized_tabular2cellular", "cellular2tabular", "tabular2cellular",

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libgymcellular_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 KIND_CELLULAR, KIND_GRIDWORLD = 0, 1
 F_NOISE, F_RNG_EPISODIC, F_REWARD_LOG2, F_GENERIC_KERNEL = 1, 4, 16, 32
 MAX_CELLS, MAX_LEVELS, N_STATS = 16, 8, 8
@@ -19,7 +19,10 @@ POLICY_RANDOM, POLICY_TABLE = 0, 1
 
 EXPORTS = ["gc_abi_version", "gc_last_error", "gc_create", "gc_destroy", "gc_set_tables",
            "gc_set_global_step", "gc_get_global_step", "gc_sync_global_step", "gc_launch_count", "gc_reset", "gc_step",
-           "gc_bind_step", "gc_step_bound", "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode", "gc_decode"]
+           "gc_bind_step", "gc_step_bound", "gc_step_many", "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode",
+           "gc_decode", "gc_encode_mixed", "gc_decode_mixed", "gc_reset_packed", "gc_step_packed", "gc_bind_step_packed",
+           "gc_step_host_packed", "gc_pack_cells", "gc_unpack_cells"]
+FLAG_UNSAFE, FLAG_TRUNCATED, FLAG_COUNT_SHIFT = 1, 2, 2
 
 
 class GcConfig(C.Structure):
@@ -33,7 +36,7 @@ class GcConfig(C.Structure):
 class GcCellTables(C.Structure):
     _fields_ = [("move", C.c_void_p), ("noisy", C.c_void_p), ("draws", C.c_void_p),
                 ("reward", C.c_void_p), ("side_effects", C.c_void_p), ("counted", C.c_void_p),
-                ("initial_state", C.c_void_p), ("reward_noisy", C.c_void_p)]
+                ("initial_state", C.c_void_p), ("reward_noisy", C.c_void_p), ("radix", C.c_void_p)]
 
 
 class GcError(RuntimeError):
@@ -77,6 +80,16 @@ def load():
     L.gc_poll_status.argtypes = [vp, vp]
     L.gc_encode.argtypes = [C.c_int, i64, i64, C.c_int32, C.c_int32, vp, vp, vp]
     L.gc_decode.argtypes = [C.c_int, i64, i64, C.c_int32, C.c_int32, vp, vp, vp]
+    i32 = C.c_int32
+    L.gc_step_many.argtypes = [vp, vp, i32, i32, vp]
+    L.gc_encode_mixed.argtypes = [C.c_int, i64, i64, i32, vp, vp, vp, vp, vp]
+    L.gc_decode_mixed.argtypes = [C.c_int, i64, i64, i32, vp, vp, vp, vp, vp]
+    L.gc_reset_packed.argtypes = [vp] * 6
+    L.gc_step_packed.argtypes = [vp, i64, i64] + [vp] * 10
+    L.gc_bind_step_packed.argtypes = [vp, i32] + [vp] * 9
+    L.gc_step_host_packed.argtypes = [vp] * 13 + [i64]
+    L.gc_pack_cells.argtypes = [C.c_int, i64, i64, i32, vp, vp, vp]
+    L.gc_unpack_cells.argtypes = [C.c_int, i64, i64, i32, vp, vp, vp]
     if L.gc_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI version mismatch: library {L.gc_abi_version()} != binding {ABI_VERSION}")
     _lib = L

@@ -75,4 +75,6 @@ class utils:  # namespace shim: gymnasium.vector.utils.batch_space
     batch_space = staticmethod(batch_space)
 
 
-__all__ = ["VectorEnv", "AutoresetMode", "batch_space", "utils"]
+from .async_vector_env import AsyncVectorEnv  # noqa: E402  (needs VectorEnv / batch_space above)
+
+__all__ = ["VectorEnv", "AsyncVectorEnv", "AutoresetMode", "batch_space", "utils"]

@@ -8,11 +8,21 @@
 #include <memory>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "gc_internal.h"
 
 namespace {
 
 thread_local char g_err[512] = "";
+
+// NVTX range around every entry point (a profiler timeline shows the host side of each call; without a
+// tool attached a push/pop is a null function-pointer test)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define GC_NVTX(name) NvtxRange nvtx_range_(name)
 
 int fail(int code, const char *fmt, ...)
 {
@@ -76,9 +86,11 @@ struct gc_env {
     uint32_t *d_step;               // device-resident global step (RNG counter of non-episodic envs)
     uint32_t *d_done;               // block-arrival counter of the step kernels
     uint2 *d_pair_lut;            // fast-path table (GC_PAIR_LUT_ENTRIES), device memory owned by the handle
+    uint2 *d_packed_lut;          // the same rules in the packed layout's index order (gc_cell_packed.cu)
     bool fast_ok;
     StepIO bound[GC_MAX_BINDINGS];  // gc_bind_step slots
-    bool bound_set[GC_MAX_BINDINGS];
+    PackedIO bound_packed[GC_MAX_BINDINGS];   // gc_bind_step_packed slots
+    int bound_set[GC_MAX_BINDINGS]; // 0 empty, 1 int8 layout, 2 packed layout
     cudaStream_t hstream[kHostStreams];
     cudaEvent_t hevent[kHostStreams];
     bool host_ready;
@@ -124,11 +136,78 @@ StepIO make_io(const gc_env *env, int64_t begin, int64_t count, const int8_t *ac
         io.round_key[2 * r + 1] = io.seed_hi + static_cast<uint32_t>(r) * 0xBB67AE85u;
     }
     io.rng_counter = static_cast<uint32_t>(env->global_step);
-    io.step_ctr = nullptr;
+    // The global step (RNG counter of the non-episodic kinds) is read from DEVICE memory by every launch, so
+    // CUDA-graph replays, pre-bound launches and host-path chunks all see the same truth.  A launch over the
+    // whole shard also advances it (done_ctr: last block to finish); a chunk of a chunked pass only reads it
+    // and the caller ticks it once after the last chunk (tick_global_step).
+    io.step_ctr = env->d_step;
     io.done_ctr = nullptr;
     io.episodic = (env->cfg.flags & GC_F_RNG_EPISODIC) ? 1 : 0;
     io.max_episode_steps = env->cfg.max_episode_steps;
     return io;
+}
+
+PackedIO make_packed_io(const gc_env *env, int64_t begin, int64_t count, const uint32_t *actions, uint32_t *state,
+                        int32_t *t, float *reward, uint32_t *index, uint8_t *flags, uint32_t *final_state,
+                        uint32_t *se_row, int64_t *stats)
+{
+    PackedIO io;
+    io.actions = actions; io.state = state; io.t = t; io.reward = reward; io.index = index; io.flags = flags;
+    io.final_state = final_state; io.se_row = se_row;
+    io.stats = reinterpret_cast<unsigned long long *>(stats);
+    io.status = env->d_status;
+    io.begin = begin; io.end = begin + count; io.ld = env->cfg.ld;
+    io.env_id_offset = env->cfg.env_id_offset;
+    const uint32_t lo = static_cast<uint32_t>(env->cfg.seed), hi = static_cast<uint32_t>(env->cfg.seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        io.round_key[2 * r] = lo + static_cast<uint32_t>(r) * 0x9E3779B9u;
+        io.round_key[2 * r + 1] = hi + static_cast<uint32_t>(r) * 0xBB67AE85u;
+    }
+    io.rng_counter = static_cast<uint32_t>(env->global_step);
+    io.step_ctr = env->d_step;
+    io.done_ctr = nullptr;
+    io.episodic = (env->cfg.flags & GC_F_RNG_EPISODIC) ? 1 : 0;
+    io.max_episode_steps = env->cfg.max_episode_steps;
+    return io;
+}
+
+int check_packed(const gc_env *env)
+{
+    if (env->cfg.kind != GC_KIND_CELLULAR || !env->fast_ok)
+        return fail(GC_ERR_INVALID, "the packed layout covers the cellular family with n_states, n_actions <= 4 "
+                                    "(and equal side-effect tables for the cells j >= 2)");
+    return GC_OK;
+}
+
+int launch_packed(gc_env *env, const PackedIO &io, cudaStream_t st)
+{
+    if (io.end <= io.begin) return GC_OK;
+    const bool draws = (env->cfg.flags & GC_F_NOISE) && env->tab.noise_thr_nz;
+    cudaError_t e = gc_launch_cell_packed_step(env->tab, io, env->d_packed_lut, draws, env->n_sm, st);
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "packed step kernel launch failed: %s", cudaGetErrorString(e));
+    env->launches += 1;
+    return GC_OK;
+}
+
+int host_streams(gc_env *env)
+{
+    if (!env->host_ready) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            GC_CUDA(cudaStreamCreateWithFlags(&env->hstream[i], cudaStreamNonBlocking));
+            GC_CUDA(cudaEventCreateWithFlags(&env->hevent[i], cudaEventDisableTiming));
+        }
+        env->host_ready = true;
+    }
+    return GC_OK;
+}
+
+// advances the device-resident global step after the last chunk of a chunked pass (stream-ordered)
+int tick_global_step(gc_env *env, cudaStream_t st)
+{
+    cudaError_t e = gc_launch_tick(env->d_step, 1u, st);
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "step-counter kernel launch failed: %s", cudaGetErrorString(e));
+    env->global_step += 1;
+    return GC_OK;
 }
 
 int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
@@ -245,6 +324,7 @@ int gc_destroy(gc_env *env)
         }
     if (env->d_status) cudaFree(env->d_status);
     if (env->d_pair_lut) cudaFree(env->d_pair_lut);
+    if (env->d_packed_lut) cudaFree(env->d_packed_lut);
     if (env->grid.lut) cudaFree(const_cast<uint32_t *>(env->grid.lut));
     delete env;
     return GC_OK;
@@ -279,14 +359,27 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
                 if (code < 0 || code > 2) return fail(GC_ERR_INVALID, "side_effects code %d not in {0,1,2}", code);
                 tab.se[j][s0 * GC_LVL_PAD + sp] = (uint8_t)code;
             }
+    // place values of the tabular index: uniform radix n_states, or the per-cell level counts of a ragged
+    // state space (generalized_space_transformations.py:1-12 takes one space per cell)
+    bool ragged = false;
+    if (t->radix) {
+        double bits = 0.0;
+        for (int c = 0; c < C; ++c) {
+            if (t->radix[c] < 1 || t->radix[c] > S) return fail(GC_ERR_INVALID, "radix[%d] = %d not in 1..n_states", c, t->radix[c]);
+            bits += std::log2((double)t->radix[c]);
+            ragged = ragged || t->radix[c] != S;
+        }
+        if (bits > 32.0 + 1e-9) return fail(GC_ERR_INVALID, "the ragged state space does not fit the 32-bit tabular index");
+    }
     uint32_t place = 1, init_index = 0;
     for (int c = 0; c < C; ++c) {
         const int lv = t->initial_state[c];
-        if (lv < 0 || lv >= S) return fail(GC_ERR_INVALID, "initial_state[%d] outside [0, %d)", c, S);
+        const int radix_c = t->radix ? t->radix[c] : S;
+        if (lv < 0 || lv >= radix_c) return fail(GC_ERR_INVALID, "initial_state[%d] outside [0, %d)", c, radix_c);
         tab.place[c] = place;
         tab.init[c] = (int8_t)lv;
         init_index += (uint32_t)lv * place;
-        place *= (uint32_t)S;
+        place *= (uint32_t)radix_c;
     }
     tab.init_index = init_index;
     for (int s = 0; s < S; ++s) if (t->counted[s]) tab.counted_mask |= 1u << s;
@@ -299,7 +392,8 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     tab.noise_thr_m1 = tab.noise_thr_nz ? static_cast<uint32_t>(tab.noise_thr - 1ull) : 0u;
 
     // ---- fast path: pair table (gc_cell_fast.cu) -------------------------------------------------
-    env->fast_ok = S <= 4 && A <= 4 && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
+    // (a ragged index needs per-cell place values: generic kernel)
+    env->fast_ok = S <= 4 && A <= 4 && !ragged && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
     for (int j = 3; j < C && env->fast_ok; ++j)
         if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
             env->fast_ok = false;
@@ -311,6 +405,11 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         GC_ON_DEVICE(env->cfg.device);
         if (!env->d_pair_lut) GC_CUDA(cudaMalloc(&env->d_pair_lut, sizeof(lut)));
         GC_CUDA(cudaMemcpy(env->d_pair_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        gc_build_packed_lut(t, C, S, A, noise, lut, tab.unsafe_spread);
+        tab.init_packed = 0;
+        for (int c = 0; c < C; ++c) tab.init_packed |= (uint32_t)(tab.init[c] & 3) << (2 * c);
+        if (!env->d_packed_lut) GC_CUDA(cudaMalloc(&env->d_packed_lut, sizeof(lut)));
+        GC_CUDA(cudaMemcpy(env->d_packed_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     }
     env->tables_set = true;
     return GC_OK;
@@ -380,17 +479,12 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
     StepIO io = make_io(env, env_begin, env_count, actions, state, t, reward, index, terminated,
                         truncated, unsafe, count, se_row, replay_u, stats);
     const bool full = env_begin == 0 && env_count == env->cfg.n_envs;
-    if (full) {                              // whole shard in one launch: device-resident step counter,
-        io.step_ctr = env->d_step;           // advanced by the kernel itself (survives graph replay)
-        io.done_ctr = env->d_done;
-    }
+    if (full) io.done_ctr = env->d_done;     // whole shard in one launch: the kernel itself advances the step
     if (int rc = launch_step(env, io, static_cast<cudaStream_t>(stream))) return rc;
     if (full) {
         env->global_step += 1;
     } else if (env_begin + env_count == env->cfg.n_envs) {                 // last chunk of a chunked pass
-        env->global_step += 1;
-        const uint32_t v = static_cast<uint32_t>(env->global_step);
-        GC_CUDA(cudaMemcpyAsync(env->d_step, &v, sizeof(v), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+        if (int rc = tick_global_step(env, static_cast<cudaStream_t>(stream))) return rc;
     }
     return GC_OK;
 }
@@ -405,20 +499,41 @@ int gc_bind_step(gc_env *env, int32_t slot, const int8_t *actions, int8_t *state
         return fail(GC_ERR_INVALID, "a required device pointer is NULL");
     env->bound[slot] = make_io(env, 0, env->cfg.n_envs, actions, state, t, reward, index, terminated, truncated,
                                unsafe, count, se_row, nullptr, stats);
-    env->bound[slot].step_ctr = env->d_step;
     env->bound[slot].done_ctr = env->d_done;
-    env->bound_set[slot] = true;
+    env->bound_set[slot] = 1;
     return GC_OK;
 }
 
+namespace {
+int launch_bound(gc_env *env, int32_t slot, cudaStream_t st)
+{
+    if (slot < 0 || slot >= GC_MAX_BINDINGS || !env->bound_set[slot])
+        return fail(GC_ERR_INVALID, "no binding in slot %d", slot);
+    if (int rc = env->bound_set[slot] == 2 ? launch_packed(env, env->bound_packed[slot], st)
+                                           : launch_step(env, env->bound[slot], st))
+        return rc;
+    env->global_step += 1;
+    return GC_OK;
+}
+}  // namespace
+
 int gc_step_bound(gc_env *env, int32_t slot, void *stream)
 {
-    if (!env || slot < 0 || slot >= GC_MAX_BINDINGS || !env->bound_set[slot])
-        return fail(GC_ERR_INVALID, "gc_step_bound: no binding in this slot");
+    if (!env) return fail(GC_ERR_INVALID, "gc_step_bound: env is NULL");
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     GC_ON_DEVICE(env->cfg.device);
-    if (int rc = launch_step(env, env->bound[slot], static_cast<cudaStream_t>(stream))) return rc;
-    env->global_step += 1;
+    return launch_bound(env, slot, static_cast<cudaStream_t>(stream));
+}
+
+int gc_step_many(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t n_steps, void *stream)
+{
+    GC_NVTX("gc_step_many");
+    if (!env || !slots || n_slots < 1 || n_steps < 0) return fail(GC_ERR_INVALID, "gc_step_many: bad arguments");
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    GC_ON_DEVICE(env->cfg.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int32_t i = 0; i < n_steps; ++i)
+        if (int rc = launch_bound(env, slots[i % n_slots], st)) return rc;
     return GC_OK;
 }
 
@@ -435,13 +550,7 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
         !d_truncated || !d_unsafe || !d_count)
         return fail(GC_ERR_INVALID, "a required pointer is NULL");
     GC_ON_DEVICE(env->cfg.device);
-    if (!env->host_ready) {
-        for (int i = 0; i < kHostStreams; ++i) {
-            GC_CUDA(cudaStreamCreateWithFlags(&env->hstream[i], cudaStreamNonBlocking));
-            GC_CUDA(cudaEventCreateWithFlags(&env->hevent[i], cudaEventDisableTiming));
-        }
-        env->host_ready = true;
-    }
+    if (int rc = host_streams(env)) return rc;
     const int64_t n = env->cfg.n_envs, ld = env->cfg.ld;
     const int C = env->cfg.n_cells;
     if (chunk_envs <= 0) chunk_envs = 1 << 20;
@@ -466,11 +575,9 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
             GC_CUDA(cudaMemcpy2DAsync(h_se_row + b, ld, d_se_row + b, ld, cnt, C, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < kHostStreams && i < k; ++i) GC_CUDA(cudaStreamSynchronize(env->hstream[i]));
-    env->global_step += 1;
-    {
-        const uint32_t v = static_cast<uint32_t>(env->global_step);
-        GC_CUDA(cudaMemcpy(env->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));
-    }
+    // every chunk read the device-resident global step; advance it once, after all of them
+    if (int rc = tick_global_step(env, env->hstream[0])) return rc;
+    GC_CUDA(cudaStreamSynchronize(env->hstream[0]));
     return GC_OK;
 }
 
@@ -548,6 +655,157 @@ int gc_decode(int device, int64_t n, int64_t ld, int32_t n_cells, int32_t radix,
     cudaError_t e = gc_launch_decode((n + 3) / 4 * 4, ld, n_cells, (uint32_t)radix, index, cells,
                                      static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(GC_ERR_CUDA, "decode kernel launch failed: %s", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+namespace {
+// radix / min: host arrays of n_cells entries; the product of the radices must fit the 32-bit index
+int check_mixed(const char *who, int64_t n, int64_t ld, int32_t n_cells, const int32_t *radix, const int32_t *min)
+{
+    if (n < 0 || ld < n || ld % 16 != 0 || n_cells < 1 || n_cells > GC_MAX_CELLS || !radix)
+        return fail(GC_ERR_INVALID, "%s: bad arguments", who);
+    double bits = 0.0;
+    for (int c = 0; c < n_cells; ++c) {
+        if (radix[c] < 1 || radix[c] > 256) return fail(GC_ERR_INVALID, "%s: radix[%d] = %d not in 1..256", who, c, radix[c]);
+        const int lo = min ? min[c] : 0;
+        if (lo < -128 || lo + radix[c] - 1 > 127)
+            return fail(GC_ERR_INVALID, "%s: cell %d spans [%d, %d], outside int8", who, c, lo, lo + radix[c] - 1);
+        bits += std::log2((double)radix[c]);
+    }
+    if (bits > 32.0 + 1e-9) return fail(GC_ERR_INVALID, "%s: the space does not fit the 32-bit tabular index", who);
+    return GC_OK;
+}
+}  // namespace
+
+int gc_encode_mixed(int device, int64_t n, int64_t ld, int32_t n_cells, const int32_t *radix, const int32_t *min,
+                    const int8_t *cells, uint32_t *index, void *stream)
+{
+    if (!cells || !index) return fail(GC_ERR_INVALID, "gc_encode_mixed: cells/index is NULL");
+    if (int rc = check_mixed("gc_encode_mixed", n, ld, n_cells, radix, min)) return rc;
+    GC_ON_DEVICE(device);
+    cudaError_t e = gc_launch_encode_mixed((n + 3) / 4 * 4, ld, n_cells, radix, min, cells, index, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "encode kernel launch failed: %s", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+int gc_decode_mixed(int device, int64_t n, int64_t ld, int32_t n_cells, const int32_t *radix, const int32_t *min,
+                    const uint32_t *index, int8_t *cells, void *stream)
+{
+    if (!cells || !index) return fail(GC_ERR_INVALID, "gc_decode_mixed: cells/index is NULL");
+    if (int rc = check_mixed("gc_decode_mixed", n, ld, n_cells, radix, min)) return rc;
+    GC_ON_DEVICE(device);
+    cudaError_t e = gc_launch_decode_mixed((n + 3) / 4 * 4, ld, n_cells, radix, min, index, cells, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "decode kernel launch failed: %s", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+// ---- packed layout (include/gym_cellular_b200.h: "Packed layout") ---------------------------------
+
+int gc_reset_packed(gc_env *env, const uint8_t *mask, uint32_t *state, int32_t *t, uint32_t *index, void *stream)
+{
+    GC_NVTX("gc_reset_packed");
+    if (int rc = check_env(env)) return rc;
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    if (int rc = check_packed(env)) return rc;
+    if (!state || !t) return fail(GC_ERR_INVALID, "state/t is NULL");
+    GC_ON_DEVICE(env->cfg.device);
+    cudaError_t e = gc_launch_reset_packed(env->tab.init_packed, env->tab.init_index, mask, state, t, index,
+                                           env->cfg.n_envs, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "reset kernel launch failed: %s", cudaGetErrorString(e));
+    env->launches += 1;
+    return GC_OK;
+}
+
+int gc_step_packed(gc_env *env, int64_t env_begin, int64_t env_count, const uint32_t *actions, uint32_t *state,
+                   int32_t *t, float *reward, uint32_t *index, uint8_t *flags, uint32_t *final_state,
+                   uint32_t *se_row, int64_t *stats, void *stream)
+{
+    if (int rc = check_env(env)) return rc;
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    if (int rc = check_packed(env)) return rc;
+    if (!actions || !state || !t || !reward || !flags) return fail(GC_ERR_INVALID, "a required device pointer is NULL");
+    if (int rc = check_range(env, env_begin, env_count)) return rc;
+    GC_ON_DEVICE(env->cfg.device);
+    PackedIO io = make_packed_io(env, env_begin, env_count, actions, state, t, reward, index, flags, final_state,
+                                 se_row, stats);
+    const bool full = env_begin == 0 && env_count == env->cfg.n_envs;
+    if (full) io.done_ctr = env->d_done;
+    if (int rc = launch_packed(env, io, static_cast<cudaStream_t>(stream))) return rc;
+    if (full) {
+        env->global_step += 1;
+    } else if (env_begin + env_count == env->cfg.n_envs) {
+        if (int rc = tick_global_step(env, static_cast<cudaStream_t>(stream))) return rc;
+    }
+    return GC_OK;
+}
+
+int gc_bind_step_packed(gc_env *env, int32_t slot, const uint32_t *actions, uint32_t *state, int32_t *t,
+                        float *reward, uint32_t *index, uint8_t *flags, uint32_t *final_state, uint32_t *se_row,
+                        int64_t *stats)
+{
+    if (int rc = check_env(env)) return rc;
+    if (int rc = check_packed(env)) return rc;
+    if (slot < 0 || slot >= GC_MAX_BINDINGS) return fail(GC_ERR_INVALID, "slot must be in [0, %d)", GC_MAX_BINDINGS);
+    if (!actions || !state || !t || !reward || !flags) return fail(GC_ERR_INVALID, "a required device pointer is NULL");
+    env->bound_packed[slot] = make_packed_io(env, 0, env->cfg.n_envs, actions, state, t, reward, index, flags,
+                                             final_state, se_row, stats);
+    env->bound_packed[slot].done_ctr = env->d_done;
+    env->bound_set[slot] = 2;
+    return GC_OK;
+}
+
+int gc_step_host_packed(gc_env *env, const uint32_t *h_actions, uint32_t *h_state, float *h_reward,
+                        uint32_t *h_index, uint8_t *h_flags, uint32_t *d_actions, uint32_t *d_state, int32_t *d_t,
+                        float *d_reward, uint32_t *d_index, uint8_t *d_flags, int64_t *d_stats, int64_t chunk_envs)
+{
+    GC_NVTX("gc_step_host_packed");
+    if (int rc = check_env(env)) return rc;
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    if (int rc = check_packed(env)) return rc;
+    if (!h_actions || !d_actions || !d_state || !d_t || !d_reward || !d_flags)
+        return fail(GC_ERR_INVALID, "a required pointer is NULL");
+    if (h_index && !d_index) return fail(GC_ERR_INVALID, "h_index needs d_index");
+    GC_ON_DEVICE(env->cfg.device);
+    if (int rc = host_streams(env)) return rc;
+    const int64_t n = env->cfg.n_envs;
+    if (chunk_envs <= 0) chunk_envs = 1 << 20;
+    chunk_envs = (chunk_envs + 15) / 16 * 16;
+    int k = 0;
+    for (int64_t b = 0; b < n; b += chunk_envs, ++k) {
+        const int64_t cnt = (b + chunk_envs < n) ? chunk_envs : (n - b);
+        cudaStream_t st = env->hstream[k % kHostStreams];
+        GC_CUDA(cudaMemcpyAsync(d_actions + b, h_actions + b, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        const PackedIO io = make_packed_io(env, b, cnt, d_actions, d_state, d_t, d_reward, d_index, d_flags,
+                                           nullptr, nullptr, d_stats);
+        if (int rc = launch_packed(env, io, st)) return rc;
+        if (h_state) GC_CUDA(cudaMemcpyAsync(h_state + b, d_state + b, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (h_reward) GC_CUDA(cudaMemcpyAsync(h_reward + b, d_reward + b, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (h_index) GC_CUDA(cudaMemcpyAsync(h_index + b, d_index + b, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (h_flags) GC_CUDA(cudaMemcpyAsync(h_flags + b, d_flags + b, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kHostStreams && i < k; ++i) GC_CUDA(cudaStreamSynchronize(env->hstream[i]));
+    if (int rc = tick_global_step(env, env->hstream[0])) return rc;
+    GC_CUDA(cudaStreamSynchronize(env->hstream[0]));
+    return GC_OK;
+}
+
+int gc_pack_cells(int device, int64_t n, int64_t ld, int32_t n_cells, const int8_t *cells, uint32_t *packed, void *stream)
+{
+    if (!cells || !packed || n < 0 || ld < n || ld % 16 != 0 || n_cells < 1 || n_cells > GC_MAX_CELLS)
+        return fail(GC_ERR_INVALID, "gc_pack_cells: bad arguments");
+    GC_ON_DEVICE(device);
+    cudaError_t e = gc_launch_pack((n + 3) / 4 * 4, ld, n_cells, cells, packed, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
+    return GC_OK;
+}
+
+int gc_unpack_cells(int device, int64_t n, int64_t ld, int32_t n_cells, const uint32_t *packed, int8_t *cells, void *stream)
+{
+    if (!cells || !packed || n < 0 || ld < n || ld % 16 != 0 || n_cells < 1 || n_cells > GC_MAX_CELLS)
+        return fail(GC_ERR_INVALID, "gc_unpack_cells: bad arguments");
+    GC_ON_DEVICE(device);
+    cudaError_t e = gc_launch_unpack((n + 3) / 4 * 4, ld, n_cells, packed, cells, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "unpack kernel launch failed: %s", cudaGetErrorString(e));
     return GC_OK;
 }
 

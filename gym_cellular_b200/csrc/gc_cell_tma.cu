@@ -255,12 +255,15 @@ template <int C>
 cudaError_t launch_tma_c(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm, cudaStream_t st)
 {
     using L = TmaLayout<C>;
-    static int per_sm = 0;
-    if (per_sm == 0) {
+    static int per_sm_dev[kMaxDevices] = {};     // per device: the shared-memory opt-in is a per-device attribute
+    const int slot = current_device_slot();
+    int per_sm = per_sm_dev[slot];
+    if (per_sm == 0 || slot == kMaxDevices - 1) {
         cudaError_t e = cudaFuncSetAttribute(cell_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return e;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cell_tma_kernel<C>, kThreads, L::kTotal) != cudaSuccess || per_sm < 1)
             per_sm = 1;
+        per_sm_dev[slot] = per_sm;
     }
     const int64_t tiles = (io.end - io.begin + kTile - 1) / kTile;
     const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;

@@ -61,7 +61,8 @@ struct ThreadStats {
 
 // Global step of the launch: device-resident when the launch covers the whole shard (so that a captured
 // CUDA graph advances its RNG counter on every replay), else the value the host passed.
-__device__ __forceinline__ uint32_t launch_step_counter(const StepIO &io)
+template <class IO>
+__device__ __forceinline__ uint32_t launch_step_counter(const IO &io)
 {
     // (not a ?: of a volatile and a plain lvalue: that makes the parameter read itself volatile and
     // sends it through a generic-address load of the kernel parameter block)
@@ -75,7 +76,7 @@ __device__ __forceinline__ uint32_t launch_step_counter(const StepIO &io)
 // the incremented value within the same launch.
 __device__ __forceinline__ void tick_step_counter(const uint32_t *step_ctr, uint32_t *done_ctr, uint32_t inc)
 {
-    if (step_ctr == nullptr) return;
+    if (done_ctr == nullptr) return;         // read-only counter: a chunk of a chunked pass (the caller ticks)
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t arrived = atomicAdd(done_ctr, 1u);
@@ -86,7 +87,8 @@ __device__ __forceinline__ void tick_step_counter(const uint32_t *step_ctr, uint
     }
 }
 
-__device__ __forceinline__ void tick_step_counter(const StepIO &io) { tick_step_counter(io.step_ctr, io.done_ctr, 1u); }
+template <class IO>
+__device__ __forceinline__ void tick_step_counter(const IO &io) { tick_step_counter(io.step_ctr, io.done_ctr, 1u); }
 
 // The same protocol with the arrival moved to the START of the kernel, so that no atomic round trip and
 // no barrier sit on the kernel's tail (they are ~1 us of a launch-bound 4 us step):
@@ -98,20 +100,23 @@ __device__ __forceinline__ void tick_step_counter(const StepIO &io) { tick_step_
 // launch reads the counter any more; the next launch starts after this one has completed.
 struct StepCounterShared { uint32_t step, arrived; };
 
-__device__ __forceinline__ void step_counter_read(const StepIO &io, StepCounterShared *s)
+template <class IO>
+__device__ __forceinline__ void step_counter_read(const IO &io, StepCounterShared *s)
 {
     if (threadIdx.x == 0) s->step = launch_step_counter(io);
 }
 
-__device__ __forceinline__ uint32_t step_counter_arrive(const StepIO &io, StepCounterShared *s)
+template <class IO>
+__device__ __forceinline__ uint32_t step_counter_arrive(const IO &io, StepCounterShared *s)
 {
-    if (threadIdx.x == 0 && io.step_ctr != nullptr) s->arrived = atomicAdd(io.done_ctr, 1u);
+    if (threadIdx.x == 0 && io.done_ctr != nullptr) s->arrived = atomicAdd(io.done_ctr, 1u);
     return s->step;
 }
 
-__device__ __forceinline__ void step_counter_finish(const StepIO &io, const StepCounterShared *s)
+template <class IO>
+__device__ __forceinline__ void step_counter_finish(const IO &io, const StepCounterShared *s)
 {
-    if (threadIdx.x == 0 && io.step_ctr != nullptr && s->arrived == gridDim.x - 1) {
+    if (threadIdx.x == 0 && io.done_ctr != nullptr && s->arrived == gridDim.x - 1) {
         *io.done_ctr = 0u;
         *const_cast<uint32_t *>(io.step_ctr) = s->step + 1u;
     }
@@ -212,6 +217,18 @@ __device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigne
 // tables are read before it.  Both instructions are no-ops in a launch without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Per-device one-time kernel setup.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the
+// CURRENT device only; a process driving several GPUs (one handle per device) must repeat it on each.
+// Returns the slot of the current device in a per-kernel table (devices beyond the table share the last
+// slot and are set up on every call).
+constexpr int kMaxDevices = 64;
+inline int current_device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
 
 inline bool pdl_enabled()
 {

@@ -243,12 +243,16 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
 template <auto Kernel>
 int grid_blocks(int64_t n, int n_sm, int smem_bytes, cudaError_t *err)
 {
-    static int per_sm = 0;
-    if (per_sm == 0) {
+    // per device: the opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute
+    static int per_sm_dev[kMaxDevices] = {};
+    const int slot = current_device_slot();
+    int per_sm = per_sm_dev[slot];
+    if (per_sm == 0 || slot == kMaxDevices - 1) {
         *err = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGridSmemBytes);
         if (*err != cudaSuccess) return 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kGridThreads, smem_bytes) != cudaSuccess || per_sm < 1)
             per_sm = 1;
+        per_sm_dev[slot] = per_sm;
     }
     const int64_t need = (n + kGridThreads * kEPT - 1) / (kGridThreads * kEPT);
     const int64_t cap = static_cast<int64_t>(n_sm) * per_sm * GC_GRID_OVERSUB;

@@ -35,6 +35,28 @@ struct StepIO {
     int32_t  max_episode_steps;
 };
 
+// Packed layout (gc_cell_packed.cu): ONE 32-bit word per env for the state and one for the action, 2 bits per
+// cell (cell c in bits 2c, 2c+1; n_states, n_actions <= 4).  For n_states == 4 the state word IS the tabular
+// index.  Per-env outputs shrink to reward + one flag byte.
+struct PackedIO {
+    const uint32_t *actions;    // [ld]
+    uint32_t *state;            // [ld] in/out
+    int32_t  *t;                // [ld] in/out
+    float    *reward;           // [ld] out
+    uint32_t *index;            // [ld] out, optional: tabular index of the returned state
+    uint8_t  *flags;            // [ld] out: bit 0 unsafe, bit 1 truncated, bits 2-6 count
+    uint32_t *final_state;      // [ld] out, optional: next state BEFORE the auto-reset (final observation)
+    uint32_t *se_row;           // [ld] out, optional: row 0 of the side-effects matrix, 2 bits per entry
+    unsigned long long *stats;
+    unsigned long long *status;
+    int64_t begin, end, ld, env_id_offset;
+    uint32_t round_key[20];
+    uint32_t rng_counter;
+    const uint32_t *step_ctr;
+    uint32_t *done_ctr;
+    int32_t episodic, max_episode_steps;
+};
+
 // K-step fused rollout (gc_rollout.cu): state stays in registers for n_steps steps, actions are
 // generated in the kernel (uniformly random, or from a tabular policy).
 struct RolloutIO {
@@ -72,6 +94,9 @@ struct CellTables {
     uint32_t noise_thr_m1;           // noise_thr - 1 (32-bit compare: fires iff thr != 0 and word <= thr - 1)
     uint32_t noise_thr_nz;
     double   noise_prob;             // for the replay path (compares doubles like the reference)
+    // packed layout (gc_cell_packed.cu)
+    uint32_t unsafe_spread[4];       // [s0']: bit 5x+4 set iff SE[j>=2][s0'][x] == unsafe (level counts live in 5-bit fields)
+    uint32_t init_packed;            // initial state, 2 bits per cell
 };
 
 struct GridParams {
@@ -105,6 +130,14 @@ cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, co
 // TMA bulk-staged variant of the deterministic pair-table step for wide envs (gc_cell_tma.cu)
 cudaError_t gc_launch_cell_tma_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
                                     cudaStream_t stream);
+// packed layout: lut = GC_PAIR_LUT_ENTRIES entries in the packed index order (gc_build_packed_lut)
+void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut, uint32_t *unsafe_spread);
+cudaError_t gc_launch_cell_packed_step(const CellTables &tab, const PackedIO &io, const uint2 *lut, bool noise,
+                                       int n_sm, cudaStream_t stream);
+cudaError_t gc_launch_reset_packed(uint32_t init_packed, uint32_t init_index, const uint8_t *mask, uint32_t *state,
+                                   int32_t *t, uint32_t *index, int64_t n, cudaStream_t stream);
+cudaError_t gc_launch_pack(int64_t n, int64_t ld, int n_cells, const int8_t *cells, uint32_t *packed, cudaStream_t stream);
+cudaError_t gc_launch_unpack(int64_t n, int64_t ld, int n_cells, const uint32_t *packed, int8_t *cells, cudaStream_t stream);
 cudaError_t gc_launch_cell_rollout(const CellTables &tab, const RolloutIO &io, const uint2 *lut, bool noise,
                                    int n_sm, cudaStream_t stream);
 cudaError_t gc_launch_grid_rollout(const GridParams &gp, const RolloutIO &io, int n_sm, cudaStream_t stream);
@@ -113,6 +146,11 @@ cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_
 cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index, const uint8_t *mask,
                             int8_t *state, int32_t *t, uint32_t *index, int64_t n, int64_t ld,
                             cudaStream_t stream);
+cudaError_t gc_launch_encode_mixed(int64_t n, int64_t ld, int n_cells, const int32_t *radix, const int32_t *min,
+                                   const int8_t *cells, uint32_t *index, cudaStream_t stream);
+cudaError_t gc_launch_decode_mixed(int64_t n, int64_t ld, int n_cells, const int32_t *radix, const int32_t *min,
+                                   const uint32_t *index, int8_t *cells, cudaStream_t stream);
+cudaError_t gc_launch_tick(uint32_t *d_step, uint32_t inc, cudaStream_t stream);
 cudaError_t gc_launch_encode(int64_t n, int64_t ld, int n_cells, uint32_t radix, const int8_t *cells,
                              uint32_t *index, cudaStream_t stream);
 cudaError_t gc_launch_decode(int64_t n, int64_t ld, int n_cells, uint32_t radix, const uint32_t *index,

@@ -193,6 +193,9 @@ reset_kernel(const __grid_constant__ InitBlock ini, const uint8_t *__restrict__ 
     }
 }
 
+// advances the device-resident global step (after the last chunk of a chunked pass)
+__global__ void tick_kernel(uint32_t *step, uint32_t inc) { *step += inc; }
+
 // Batched mixed-radix codec, uniform radix (generalized_space_transformations.py:1-23).
 // index = sum_c cells[c] * radix^c  (cell 0 least significant); 32-bit unsigned arithmetic.
 __global__ void __launch_bounds__(kThreads)
@@ -234,7 +237,78 @@ decode_kernel(int64_t n, int64_t ld, int n_cells, uint32_t radix, const uint32_t
     }
 }
 
+// The reference's codec proper: a per-cell space list with arbitrary minimum and length
+// (generalized_space_transformations.py:1-12: digit c = cells[c] - min(space[c]), radix c = len(space[c]);
+// :15-23: the inverse by repeated modulo / floor division), batched.  32-bit unsigned index.
+struct MixedRadix { uint32_t radix[GC_MAX_CELLS]; int32_t min[GC_MAX_CELLS]; int32_t n_cells; };
+
+__global__ void __launch_bounds__(kThreads)
+encode_mixed_kernel(const __grid_constant__ MixedRadix mr, int64_t n, int64_t ld, const int8_t *__restrict__ cells,
+                    uint32_t *__restrict__ index)
+{
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT; e0 < n; e0 += stride) {
+        uint32_t idx[kEPT] = {0, 0, 0, 0};
+        uint32_t place = 1;
+        for (int c = 0; c < mr.n_cells; ++c) {
+            const uint32_t w = ld_stream_u32(cells + c * ld + e0);
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                const int digit = static_cast<int>(static_cast<int8_t>(byte_of(w, e))) - mr.min[c];
+                idx[e] += static_cast<uint32_t>(digit) * place;
+            }
+            place *= mr.radix[c];
+        }
+        st_stream_v4(index + e0, make_int4(idx[0], idx[1], idx[2], idx[3]));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+decode_mixed_kernel(const __grid_constant__ MixedRadix mr, int64_t n, int64_t ld, const uint32_t *__restrict__ index,
+                    int8_t *__restrict__ cells)
+{
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    for (int64_t e0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT; e0 < n; e0 += stride) {
+        const int4 v = ld_stream_v4(index + e0);
+        uint32_t idx[kEPT] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y),
+                              static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
+        for (int c = 0; c < mr.n_cells; ++c) {
+            const uint32_t radix = mr.radix[c];
+            uint32_t w = 0;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                const int level = static_cast<int>(idx[e] % radix) + mr.min[c];
+                w |= (static_cast<uint32_t>(level) & 0xFFu) << (8 * e);
+                idx[e] /= radix;
+            }
+            st_stream_u32(cells + c * ld + e0, w);
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t gc_launch_encode_mixed(int64_t n, int64_t ld, int n_cells, const int32_t *radix, const int32_t *min,
+                                   const int8_t *cells, uint32_t *index, cudaStream_t st)
+{
+    MixedRadix mr = {};
+    for (int c = 0; c < n_cells; ++c) { mr.radix[c] = static_cast<uint32_t>(radix[c]); mr.min[c] = min ? min[c] : 0; }
+    mr.n_cells = n_cells;
+    const int64_t need = (n + kThreads * kEPT - 1) / (kThreads * kEPT);
+    encode_mixed_kernel<<<static_cast<int>(need < 1 ? 1 : (need > 65535 ? 65535 : need)), kThreads, 0, st>>>(mr, n, ld, cells, index);
+    return cudaGetLastError();
+}
+
+cudaError_t gc_launch_decode_mixed(int64_t n, int64_t ld, int n_cells, const int32_t *radix, const int32_t *min,
+                                   const uint32_t *index, int8_t *cells, cudaStream_t st)
+{
+    MixedRadix mr = {};
+    for (int c = 0; c < n_cells; ++c) { mr.radix[c] = static_cast<uint32_t>(radix[c]); mr.min[c] = min ? min[c] : 0; }
+    mr.n_cells = n_cells;
+    const int64_t need = (n + kThreads * kEPT - 1) / (kThreads * kEPT);
+    decode_mixed_kernel<<<static_cast<int>(need < 1 ? 1 : (need > 65535 ? 65535 : need)), kThreads, 0, st>>>(mr, n, ld, index, cells);
+    return cudaGetLastError();
+}
 
 cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng_mode, int n_sm, cudaStream_t st)
 {
@@ -264,6 +338,12 @@ cudaError_t gc_launch_reset(int n_cells, const int8_t *init, uint32_t init_index
     const int64_t need = (n + kThreads * kEPT - 1) / (kThreads * kEPT);
     reset_kernel<<<static_cast<int>(need < 1 ? 1 : (need > 65535 ? 65535 : need)), kThreads, 0, st>>>(
         ini, mask, state, t, index, n, ld);
+    return cudaGetLastError();
+}
+
+cudaError_t gc_launch_tick(uint32_t *d_step, uint32_t inc, cudaStream_t st)
+{
+    tick_kernel<<<1, 1, 0, st>>>(d_step, inc);
     return cudaGetLastError();
 }
 

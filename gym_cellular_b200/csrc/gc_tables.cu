@@ -94,3 +94,55 @@ void gc_build_pair_lut(const gc_cell_tables *t, int C, int S, int A, bool noise,
             for (int x = 0; x < S; ++x)
                 if (se(2, s0, x) == 2) *unsafe_rows |= (1u << x) << (8 * s0);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Cellular family, packed layout (gc_cell_packed.cu): the same pair / single-cell rules, indexed the way
+// the packed words deliver the digits and with the info word laid out for whole-word accumulation.
+//   pair index   p = (s_c | s_d << 2) | (a_c | a_d << 2) << 4 | fire_c << 8 | fire_d << 9
+//   single index p = s | a << 2 | fire << 4                       (entries GC_PAIR_LUT_PAIRS ..)
+//   .x  bits  0-4 / 5-9 / 10-14 / 15-19   how many of the entry's next levels equal level 0 / 1 / 2 / 3
+//       bits 20-24  how many of them count towards the incidence          (cells3states3actions3.py:159-162)
+//       bit  25     row-0 entries 0 and 1 of the side-effects matrix hold 'unsafe' for (s'_c, s'_d)
+//                   (meaningful for the pair (cell 0, cell 1); single entry: for a 1-cell env)   (:157-212)
+//       bits 28-31  next levels s'_c | s'_d << 2                                                 (:133-154)
+//   .y  reward contribution (float)                                                              (:9-45)
+// The sum of the .x words of an env's entries has no carries between the fields (<= 16 cells), and the
+// nibble sits on top so that whatever its sum carries out of is discarded.
+void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut, uint32_t *unsafe_spread)
+{
+    auto ok = [&](int s, int a) { return s < S && a < A; };
+    auto nxt = [&](int s, int a, int fire) {
+        if (!ok(s, a)) return 0;
+        if (noise && fire && t->draws[s * A + a]) return (int)t->noisy[s * A + a];
+        return (int)t->move[s * A + a];
+    };
+    auto rw = [&](int s, int a, int fire) {
+        if (!ok(s, a)) return 0.0;
+        if (noise && fire && t->draws[s * A + a] && t->reward_noisy) return (double)t->reward_noisy[s * A + a];
+        return (double)t->reward[s * A + a];
+    };
+    auto se = [&](int j, int s0, int sp) { return (int)t->side_effects[((size_t)j * S + s0) * S + sp]; };
+    auto info = [&](int n) { return (1u << (5 * n)) | (t->counted[n] ? (1u << 20) : 0u); };
+    for (int p = 0; p < GC_PAIR_LUT_PAIRS; ++p) {
+        const int sc = p & 3, sd = (p >> 2) & 3, ac = (p >> 4) & 3, ad = (p >> 6) & 3;
+        const int fc = (p >> 8) & 1, fd = (p >> 9) & 1;
+        const int nc = nxt(sc, ac, fc), nd = nxt(sd, ad, fd);
+        const uint32_t uns01 = (C >= 2 && (se(0, nc, nd) == 2 || se(1, nc, nd) == 2)) ? 1u : 0u;
+        lut[p].x = (info(nc) + info(nd)) | (uns01 << 25) | ((uint32_t)(nc | (nd << 2)) << 28);
+        const float f = (float)(rw(sc, ac, fc) + rw(sd, ad, fd));
+        std::memcpy(&lut[p].y, &f, sizeof(f));
+    }
+    for (int p = 0; p < 32; ++p) {
+        const int s = p & 3, a = (p >> 2) & 3, n = nxt(s, a, (p >> 4) & 1);
+        const uint32_t uns0 = (C == 1 && se(0, n, n) == 2) ? 1u : 0u;
+        lut[GC_PAIR_LUT_PAIRS + p].x = info(n) | (uns0 << 25) | ((uint32_t)n << 28);
+        const float f = (float)rw(s, a, (p >> 4) & 1);
+        std::memcpy(&lut[GC_PAIR_LUT_PAIRS + p].y, &f, sizeof(f));
+    }
+    for (int s0 = 0; s0 < 4; ++s0) {
+        unsafe_spread[s0] = 0;
+        if (C >= 3 && s0 < S)
+            for (int x = 0; x < S; ++x)
+                if (se(2, s0, x) == 2) unsafe_spread[s0] |= 1u << (5 * x + 4);
+    }
+}

@@ -64,6 +64,15 @@ class StatsReducer:
             self._work = dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         return self
 
+    def wait(self):
+        """Orders the current stream after the pending reduction (no host synchronisation)."""
+        if self._work is not None:
+            self._work.wait()
+            if self._buf.is_cuda:
+                torch.cuda.current_stream(self._buf.device).wait_stream(self._stream)
+            self._work = None
+        return self
+
     def result(self):
         """Global totals as a dict (waits for the reduction)."""
         if self._work is not None:

@@ -79,14 +79,22 @@ class CellReward:
         self.__name__ = name
         self.spec = spec
         self.log2 = log2
+        self.n_states, self.n_actions = n_states, n_actions
         self._default = _reward_table(spec, n_states, n_actions)
 
     def table(self, n_states, n_actions):
         return _reward_table(self.spec, n_states, n_actions)
 
+    def for_shape(self, n_states, n_actions):
+        """The same reward bound to an env shape: which level plays the 'polarised' role depends on the
+        number of levels, so the callable handed to agents (`prior_knowledge.reward_func`) must know it --
+        it cannot be guessed from the values of one (state, action) pair."""
+        if (n_states, n_actions) == (self.n_states, self.n_actions):
+            return self
+        return CellReward(self.__name__, self.spec, self.log2, n_states, n_actions)
+
     def __call__(self, state, action, next_state=None):
-        n_states = max(3, max(state) + 1, max(action) + 1)
-        tab = self._default if n_states == 3 else self.table(n_states, n_states)
+        tab = self._default
         reward = 0.0
         for s, a in zip(state, action):
             reward += tab[s, a]
@@ -133,6 +141,14 @@ def _tabulate_callable(f, n_cells, n_states, n_actions):
                 tab[s, a] = g(f(tuple(st), tuple(ac), tuple(st))) - base + cell_base
         return tab
     rng = np.random.default_rng(0)
+    # a device table is a function of (level, action) only: reject rewards that look at next_state
+    for _ in range(64):
+        st = tuple(int(x) for x in rng.integers(0, n_states, n_cells))
+        ac = tuple(int(x) for x in rng.integers(0, n_actions, n_cells))
+        ns = tuple(int(x) for x in rng.integers(0, n_states, n_cells))
+        if float(f(st, ac, ns)) != float(f(st, ac, st)):
+            raise ValueError("reward_func depends on next_state; only per-cell functions of (level, action) can be "
+                             "lowered to a device table (pass cell_tables with reward_noisy for next-level rewards)")
     for log2, g in ((False, lambda x: float(x)), (True, lambda x: float(2.0 ** x - 1.0))):
         tab = probe(g)
         ok = True

@@ -115,6 +115,8 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if kind == "cellular":
             if reward_func is None:
                 reward_func = tables.nonlinear_right_polarizing if stochastic else tables.right_polarizing
+            if isinstance(reward_func, tables.CellReward):     # bind the shape: the host callable must agree with the device table
+                reward_func = reward_func.for_shape(self.n_states, self.n_actions)
             self.reward_func = reward_func
             self.reward_table, self.reward_log2 = tables.lower_reward(reward_func, self.n_cells, self.n_states, self.n_actions)
             if stochastic:
@@ -138,7 +140,21 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if kind == "cellular":
             self._set_tables()
 
-        # --- device buffers (caller-owned as far as the library is concerned) ---------------
+        self._collect_stats = bool(collect_stats)
+        self._alloc_device_buffers()
+        self._host = None                                 # pinned mirrors, allocated on first host step
+
+        # --- spaces -------------------------------------------------------------------------
+        sp = gym.spaces
+        self.single_observation_space = sp.Tuple([sp.Discrete(self.n_states) for _ in range(self.n_cells)])
+        self.single_action_space = sp.Tuple([sp.Discrete(self.n_actions) for _ in range(self.n_cells)])
+        self._batched_spaces = None          # built on first access: 2 x n_cells arrays of num_envs int64
+        self.closed = False
+        self._build_views()
+        self.reset()
+
+    def _alloc_device_buffers(self):
+        """Device buffers (caller-owned as far as the library is concerned)."""
         dev, ld, Cn = self.device, self.ld, self.n_cells
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
         self._state = z(Cn, ld, dtype=torch.int8)
@@ -151,17 +167,7 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         self._unsafe = z(ld, dtype=torch.uint8)
         self._count = z(ld, dtype=torch.uint8)
         self._se_row = z(Cn, ld, dtype=torch.int8) if self.emit_side_effects else None
-        self._stats = z(_lib.N_STATS, dtype=torch.int64) if collect_stats else None
-        self._host = None                                 # pinned mirrors, allocated on first host step
-
-        # --- spaces -------------------------------------------------------------------------
-        sp = gym.spaces
-        self.single_observation_space = sp.Tuple([sp.Discrete(self.n_states) for _ in range(Cn)])
-        self.single_action_space = sp.Tuple([sp.Discrete(self.n_actions) for _ in range(Cn)])
-        self._batched_spaces = None          # built on first access: 2 x n_cells arrays of num_envs int64
-        self.closed = False
-        self._build_views()
-        self.reset()
+        self._stats = z(_lib.N_STATS, dtype=torch.int64) if self._collect_stats else None
 
     def _spaces(self):
         if self._batched_spaces is None:
@@ -344,7 +350,9 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                 self._se_row[0].fill_(tables.SAFE)
             else:
                 self._se_row.fill_(tables.SAFE)
-        self._lib.gc_set_global_step(self._h, 0)
+        # the global step (RNG counter of the non-episodic kinds: grid world, DeepExplorationDebug) is NOT
+        # rewound: the reference never re-seeds these envs (grid_world.py:97-104), every episode draws
+        # fresh numbers.  The episodic kinds count from the per-env episode step, which reset() zeroes.
         return self._obs_device(), self._infos_device()
 
     def reset_envs(self, mask):
@@ -388,27 +396,34 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe), _ptr(self._count),
             _ptr(self._se_row), _ptr(ru), _ptr(self._stats), self._stream()))
 
+    def _bind(self, actions=None):
+        """Stores the pointer set of a full-shard step in one of the handle's 16 slots; returns the slot."""
+        a = self._actions if actions is None else actions
+        if a.dtype != torch.int8 or a.shape != (self.n_cells, self.ld) or not a.is_contiguous() or a.device != self.device:
+            raise ValueError(f"bind_step needs a contiguous int8 tensor of shape {(self.n_cells, self.ld)} on {self.device}")
+        slot = getattr(self, "_n_bound", 0)
+        if slot >= 16:                      # GC_MAX_BINDINGS: the pointer set lives in the handle
+            raise RuntimeError("all 16 binding slots of the handle are in use")
+        self._n_bound = slot + 1
+        _lib.check(self._lib.gc_bind_step(self._h, slot, _ptr(a), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
+                                          _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated),
+                                          _ptr(self._unsafe), _ptr(self._count), _ptr(self._se_row), _ptr(self._stats)))
+        self.__dict__.setdefault("_bound_keepalive", []).append(a)
+        return slot
+
     def bind_step(self, actions=None, stream=None):
         """Returns a zero-argument callable that launches one step with all ctypes arguments
         pre-bound (for tight rollout loops: ~4-6 us of host time per step) -- on `stream`
         (a torch.cuda.Stream, its handle looked up once) or, by default, on whatever stream is
         current at each call.  `actions`: an int8 device tensor [n_cells, ld] kept alive by the
         caller, or None for `action_buffer`."""
-        a = self._actions if actions is None else actions
-        if a.dtype != torch.int8 or a.shape != (self.n_cells, self.ld) or not a.is_contiguous() or a.device != self.device:
-            raise ValueError(f"bind_step needs a contiguous int8 tensor of shape {(self.n_cells, self.ld)} on {self.device}")
-        slot = getattr(self, "_n_bound", 0)
         check, dev, current_stream = _lib.check, self.device, torch.cuda.current_stream
         if stream is not None:
             if stream.device != self.device:
                 raise ValueError(f"stream lives on {stream.device}, the env on {self.device}")
             pinned = stream.cuda_stream
-            current_stream = lambda _dev: stream          # noqa: E731  (keeps the stream object alive, too)
-        if slot < 16:                      # GC_MAX_BINDINGS: the pointer set lives in the handle
-            self._n_bound = slot + 1
-            check(self._lib.gc_bind_step(self._h, slot, _ptr(a), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
-                                         _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated),
-                                         _ptr(self._unsafe), _ptr(self._count), _ptr(self._se_row), _ptr(self._stats)))
+        if getattr(self, "_n_bound", 0) < 16:
+            slot = self._bind(actions)
             fn, h = self._lib.gc_step_bound, self._h
 
             if stream is not None:
@@ -416,23 +431,43 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                     rc = fn(h, slot, pinned)
                     if rc:
                         check(rc)
+                launch.stream, launch.slot = stream, slot     # keeps the stream object alive, too
                 return launch
 
             def launch():
                 rc = fn(h, slot, current_stream(dev).cuda_stream)
                 if rc:
                     check(rc)
+            launch.slot = slot
             return launch
+        a = self._actions if actions is None else actions
+        if a.dtype != torch.int8 or a.shape != (self.n_cells, self.ld) or not a.is_contiguous() or a.device != self.device:
+            raise ValueError(f"bind_step needs a contiguous int8 tensor of shape {(self.n_cells, self.ld)} on {self.device}")
         fn = self._lib.gc_step
         args = (self._h, 0, self.num_envs, _ptr(a), _ptr(self._state), _ptr(self._t), _ptr(self._reward),
                 _ptr(self._index), _ptr(self._terminated), _ptr(self._truncated), _ptr(self._unsafe),
                 _ptr(self._count), _ptr(self._se_row), None, _ptr(self._stats))
+        if stream is not None:
+            current_stream = lambda _dev: stream          # noqa: E731
 
         def launch():
             rc = fn(*args, current_stream(dev).cuda_stream)
             if rc:
                 check(rc)
         return launch
+
+    def step_many(self, slots, n_steps, stream=None):
+        """`n_steps` pre-bound steps back to back in ONE foreign call (gc_step_many): step i launches the
+        binding `slots[i % len(slots)]` (slots from `_bind` / `bind_step(...).slot`).  The launches are
+        chained by programmatic dependent launch and no Python runs between them -- the per-step loop of
+        launch-bound batch sizes without capturing a CUDA graph."""
+        key = tuple(int(x) for x in slots)
+        cache = self.__dict__.setdefault("_slot_arrays", {})
+        arr = cache.get(key)
+        if arr is None:
+            arr = cache[key] = (C.c_int32 * len(key))(*key)
+        st = (torch.cuda.current_stream(self.device) if stream is None else stream).cuda_stream
+        _lib.check(self._lib.gc_step_many(self._h, arr, len(key), int(n_steps), st))
 
     def rollout(self, n_steps, policy=None):
         """Fused K-step rollout: `n_steps` steps per env inside one kernel, actions generated on the
@@ -453,7 +488,6 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         _lib.check(self._lib.gc_rollout(self._h, int(n_steps), kind, _ptr(ptab), _ptr(self._state), _ptr(self._t),
                                         _ptr(self._index), _ptr(self._ro_ret), _ptr(self._ro_unsafe), _ptr(self._stats),
                                         self._stream()))
-        self._graph_dirty = True
         return self._ro_ret[:n], self._ro_unsafe[:n]
 
     def capture_steps(self, action_ring):
@@ -467,13 +501,13 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         with torch.cuda.graph(graph):
             for call in calls:
                 call()
-        self._graph_dirty = True            # host mirror of the step counter is refreshed on demand
         return graph
 
     def sync_step_counter(self):
-        """Refreshes the host mirror of the global step after CUDA-graph replays; returns it."""
+        """Reads the device-resident global step into the host mirror and returns it.  (The kernels of
+        every path -- step, bound step, graph replay, host-path chunks -- read the device word; the mirror
+        only serves state_dict() and diagnostics.)"""
         _lib.check(self._lib.gc_sync_global_step(self._h, self._stream()))
-        self._graph_dirty = False
         return int(self._lib.gc_get_global_step(self._h))
 
     @property
@@ -583,8 +617,6 @@ class CellularVectorEnv(gym.vector.VectorEnv):
             h["actions"][:, :n] = actions.T
         else:
             raise ValueError(f"actions must have shape {(self.n_cells, n)} or {(n, self.n_cells)}")
-        if getattr(self, "_graph_dirty", False):
-            self.sync_step_counter()
         torch.cuda.current_stream(self.device).synchronize()     # resident state must be settled
         H = self._host
         # 'terminated' is constant False (cells3states3actions3.py:122, grid_world.py:113) and 'truncated' is
@@ -605,16 +637,32 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         return obs, h["reward"][:n], h["terminated"][:n].view(np.bool_), h["truncated"][:n].view(np.bool_), infos
 
 
-def make_vector_env(env_id, num_envs, **kwargs):
-    """`gymnasium.make_vec`-style constructor from a registered id ('gym_cellular/<Name>-v0')."""
+def make_vector_env(env_id, num_envs, layout="int8", **kwargs):
+    """`gymnasium.make_vec`-style constructor from a registered id ('gym_cellular/<Name>-v0'): all seven
+    ids of the reference (gym_cellular/__init__.py:4-45).  `layout='packed'` selects the packed-word layout
+    (`PackedCellularVectorEnv`; every id but GridWorld)."""
+    from . import tables
     name = env_id.split("/")[-1]
-    if name not in _FAMILIES:
-        raise ValueError(f"{env_id} has no batched CUDA implementation (have: {sorted(_FAMILIES)})")
+    debug = {"Debug-v0": tables.debug_tables, "DeepPlanningDebug-v0": tables.deep_planning_tables,
+             "DeepExplorationDebug-v0": tables.deep_exploration_tables}
+    if name not in _FAMILIES and name not in debug:
+        raise ValueError(f"{env_id} has no batched CUDA implementation (have: {sorted(_FAMILIES) + sorted(debug)})")
+    if layout not in ("int8", "packed"):
+        raise ValueError("layout must be 'int8' or 'packed'")
+    cls = CellularVectorEnv
+    if layout == "packed":
+        from .packed_env import PackedCellularVectorEnv as cls
+    if name in debug:
+        if name == "DeepExplorationDebug-v0":
+            kwargs.setdefault("rng_episodic", False)    # the reference never re-seeds it (debug/deep_exploration.py:49)
+        return cls(kind="cellular", num_envs=num_envs, cell_tables=debug[name](), **kwargs)
     kind, n_cells, n_states, n_actions, stochastic = _FAMILIES[name]
     if kind == "gridworld":
+        if layout == "packed":
+            raise ValueError("the packed layout covers the cellular family; GridWorld uses the int8 layout")
         return CellularVectorEnv(kind="gridworld", num_envs=num_envs, **kwargs)
     kwargs.setdefault("n_cells", n_cells)
     kwargs.setdefault("n_states", n_states)
     kwargs.setdefault("n_actions", n_actions)
     kwargs.setdefault("stochastic", stochastic)
-    return CellularVectorEnv(kind="cellular", num_envs=num_envs, **kwargs)
+    return cls(kind="cellular", num_envs=num_envs, **kwargs)

@@ -19,6 +19,10 @@
  *   gc_reset   <- *.reset                         cells3states3actions3.py:99-113, grid_world.py:97-104
  *   gc_encode  <- generalized_cellular2tabular    gym_cellular/envs/utils/generalized_space_transformations.py:1-12
  *   gc_decode  <- generalized_tabular2cellular    gym_cellular/envs/utils/generalized_space_transformations.py:15-23
+ *   gc_encode_mixed / gc_decode_mixed <- the same two functions with a per-cell space list (arbitrary
+ *                 minimum and length per cell), as the reference defines them
+ *   gc_step_packed / gc_step_host_packed <- the same step() in the packed layout (one 32-bit word per
+ *                 env for the joint state, one for the joint action: "Packed layout" below)
  *   gc_step_host <- the same step() seen from a host caller (numpy in, numpy out): H2D of the
  *                 actions, the kernel, D2H of observation/reward/flags, pipelined in chunks.
  *
@@ -45,7 +49,7 @@
 extern "C" {
 #endif
 
-#define GC_ABI_VERSION 1
+#define GC_ABI_VERSION 2
 
 typedef struct gc_env gc_env;
 
@@ -121,6 +125,9 @@ typedef struct {
     const uint8_t *counted;
     const int8_t  *initial_state;
     const float   *reward_noisy;
+    const int32_t *radix;        /* optional [C]: levels of each cell for the tabular index of a ragged state
+                                    space (radix[c] <= n_states; the moves must keep cell c below radix[c]);
+                                    NULL = n_states for every cell */
 } gc_cell_tables;
 
 int         gc_abi_version(void);
@@ -178,6 +185,10 @@ int gc_bind_step(gc_env *env, int32_t slot, const int8_t *actions, int8_t *state
                  uint32_t *index, uint8_t *terminated, uint8_t *truncated, uint8_t *unsafe, uint8_t *count,
                  int8_t *se_row, int64_t *stats);
 int gc_step_bound(gc_env *env, int32_t slot, void *stream);
+/* n_steps pre-bound steps back to back in ONE foreign call: step i launches slot slots[i % n_slots]
+ * (int8 or packed bindings).  The launches are chained with programmatic dependent launch, no host code runs
+ * between them: the per-step loop of launch-bound batch sizes (BASELINE configs 2 and 3) without a CUDA graph. */
+int gc_step_many(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t n_steps, void *stream);
 
 /* The same step for a HOST caller: h_* are host buffers (pinned for full speed) in the same
  * layouts with row stride ld; d_* the caller-owned resident device arrays.  Copies the actions in,
@@ -190,6 +201,44 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
                  float *d_reward, uint32_t *d_index, uint8_t *d_terminated, uint8_t *d_truncated,
                  uint8_t *d_unsafe, uint8_t *d_count, int8_t *d_se_row, int64_t *d_stats,
                  int64_t chunk_envs);
+
+/* ---- Packed layout -------------------------------------------------------------------------------
+ * Cellular family with n_states, n_actions <= 4 (every polarisation env of the reference and the 16 x 4
+ * scale-up).  The joint state and the joint action of an env are ONE uint32 each, 2 bits per cell, cell c in
+ * bits 2c and 2c+1 -- for n_states == 4 the state word is the reference's tabular index itself
+ * (generalized_space_transformations.py:1-12: cell 0 least significant).  Per-env outputs shrink to the
+ * reward and one flag byte, so an env-step moves 25 bytes through HBM instead of 3 n_cells + 20 and 4 bytes
+ * in / 9 bytes out over the host link instead of n_cells / n_cells + 10:
+ *   actions     uint32 [ld]  in      joint action word
+ *   state       uint32 [ld]  in/out  joint state word
+ *   t           int32  [ld]  in/out  episode step
+ *   reward      float  [ld]  out
+ *   index       uint32 [ld]  out     optional: tabular index of the returned state (== state when n_states == 4)
+ *   flags       uint8  [ld]  out     bit 0 unsafe, bit 1 truncated, bits 2-6 count (GC_FLAG_*); terminated is
+ *                                    always false (cells3states3actions3.py:121) and has no bit
+ *   final_state uint32 [ld]  out     optional: the next state BEFORE the time-limit auto-reset (gymnasium's
+ *                                    final observation; equals `state` where truncated == 0)
+ *   se_row      uint32 [ld]  out     optional: row 0 of the side-effects matrix, 2 bits per entry
+ * Same semantics, same Philox draws and bit-identical results as gc_step on the int8 layout
+ * (gc_pack_cells / gc_unpack_cells convert).  Replay of recorded uniforms is offered by gc_step only. */
+#define GC_FLAG_UNSAFE      1u
+#define GC_FLAG_TRUNCATED   2u
+#define GC_FLAG_COUNT_SHIFT 2
+int gc_reset_packed(gc_env *env, const uint8_t *mask, uint32_t *state, int32_t *t, uint32_t *index, void *stream);
+int gc_step_packed(gc_env *env, int64_t env_begin, int64_t env_count, const uint32_t *actions, uint32_t *state,
+                   int32_t *t, float *reward, uint32_t *index, uint8_t *flags, uint32_t *final_state,
+                   uint32_t *se_row, int64_t *stats, void *stream);
+int gc_bind_step_packed(gc_env *env, int32_t slot, const uint32_t *actions, uint32_t *state, int32_t *t,
+                        float *reward, uint32_t *index, uint8_t *flags, uint32_t *final_state, uint32_t *se_row,
+                        int64_t *stats);
+/* Host caller, packed wire format: h_actions in (4 bytes per env), h_state / h_reward / h_flags (and h_index
+ * when asked for) out; chunks pipelined over the handle's streams like gc_step_host. */
+int gc_step_host_packed(gc_env *env, const uint32_t *h_actions, uint32_t *h_state, float *h_reward,
+                        uint32_t *h_index, uint8_t *h_flags, uint32_t *d_actions, uint32_t *d_state, int32_t *d_t,
+                        float *d_reward, uint32_t *d_index, uint8_t *d_flags, int64_t *d_stats, int64_t chunk_envs);
+/* int8 [n_cells][ld] levels <-> packed words [ld] */
+int gc_pack_cells(int device, int64_t n, int64_t ld, int32_t n_cells, const int8_t *cells, uint32_t *packed, void *stream);
+int gc_unpack_cells(int device, int64_t n, int64_t ld, int32_t n_cells, const uint32_t *packed, int8_t *cells, void *stream);
 
 /* K-step fused rollout (the caller's loop around step(): pick an action, step, accumulate).  Runs
  * n_steps consecutive steps for every env of the shard inside ONE kernel; the state stays in
@@ -217,6 +266,15 @@ int gc_encode(int device, int64_t n, int64_t ld, int32_t n_cells, int32_t radix,
               uint32_t *index, void *stream);
 int gc_decode(int device, int64_t n, int64_t ld, int32_t n_cells, int32_t radix, const uint32_t *index,
               int8_t *cells, void *stream);
+
+/* The reference's codec with its per-cell space list (generalized_space_transformations.py:1-23): cell c
+ * takes the values min[c] .. min[c] + radix[c] - 1 (radix, min: HOST arrays of n_cells entries, min may be
+ * NULL = all zero); index = sum_c (cells[c] - min[c]) * prod_{k<c} radix[k].  The product of the radices
+ * must fit the 32-bit index (the reference works on unbounded Python ints). */
+int gc_encode_mixed(int device, int64_t n, int64_t ld, int32_t n_cells, const int32_t *radix, const int32_t *min,
+                    const int8_t *cells, uint32_t *index, void *stream);
+int gc_decode_mixed(int device, int64_t n, int64_t ld, int32_t n_cells, const int32_t *radix, const int32_t *min,
+                    const uint32_t *index, int8_t *cells, void *stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device and the built library: on a CUDA-less machine a plain `pytest tests`
+    skips them instead of failing (the driver selects them explicitly with -m gpu on the B200 box)."""
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    lib = os.path.join(REPO, "gym_cellular_b200", "lib", "libgymcellular_b200.so")
+    if have_gpu and os.path.exists(lib):
+        return
+    reason = "needs a CUDA device" if not have_gpu else "libgymcellular_b200.so has not been built"
+    skip = pytest.mark.skip(reason=reason)
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_pol():
     return np.load(os.path.join(GOLDEN, "polarisation.npz"))

@@ -32,7 +32,7 @@ def test_struct_layout_matches_header():
     # gc_config: 8 x 32-bit, then 3 x int64, uint64, 2 x double -> 80 bytes, no padding
     assert C.sizeof(_lib.GcConfig) == 8 * 4 + 4 * 8 + 2 * 8 == 80
     assert _lib.GcConfig.n_envs.offset == 32 and _lib.GcConfig.seed.offset == 56
-    assert C.sizeof(_lib.GcCellTables) == 8 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_lib.GcCellTables) == 9 * C.sizeof(C.c_void_p)
     header = open(os.path.join(REPO, "include", "gym_cellular_b200.h")).read()
     for name, val in (("GC_F_NOISE", _lib.F_NOISE), ("GC_F_RNG_EPISODIC", _lib.F_RNG_EPISODIC),
                       ("GC_F_REWARD_LOG2", _lib.F_REWARD_LOG2), ("GC_F_GENERIC_KERNEL", _lib.F_GENERIC_KERNEL), ("GC_MAX_CELLS", _lib.MAX_CELLS),

@@ -868,3 +868,47 @@ def test_example_plan_and_rollout(B):
     finally:
         sys.argv = argv
     assert res["planned"][0] > res["random"][0] * 1.5
+
+
+def test_gridworld_episodes_after_reset_draw_fresh_noise(B, O):
+    """The reference never re-seeds grid world (grid_world.py:97-104): after reset() the dispersal events
+    must NOT replay the previous episode's.  The global step keeps counting across reset(), as the oracle's."""
+    n = 4096
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=3, dispersal_prob=0.2)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=3, dispersal_prob=0.2)
+    rng = np.random.default_rng(8)
+    acts = []
+    for _ in range(6):
+        a = np.full((2, n), 4, np.int8)
+        a[rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+        acts.append(a)
+    episodes = []
+    for ep in range(2):
+        env.reset()
+        ora.reset()
+        traj = []
+        for a in acts:
+            env.step_device(dev(a))
+            ora.step(a)
+            assert_matches_oracle(env, ora)
+            traj.append(host(env.state).copy())
+        episodes.append(np.stack(traj))
+    assert env.sync_step_counter() == 12
+    assert (episodes[0] != episodes[1]).any()          # same actions, different dispersal draws
+
+
+def test_gridworld_staged_table_on_second_device(B, O):
+    """The staged-table grid-world kernel (> 48 KB of dynamic shared memory: a per-device opt-in) on two
+    devices of one process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 1 << 21                                            # above the staging threshold
+    rng = np.random.default_rng(9)
+    a = np.full((2, n), 4, np.int8)
+    a[rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=4)
+    ora.step_parallel(a, __import__("os").cpu_count() or 1)
+    for d in ("cuda:0", "cuda:1"):
+        env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=4, device=d)
+        env.step_device(torch.from_numpy(a).to(d))
+        assert (host(env.state) == ora.state).all() and (host(env._reward[:n]) == ora.reward).all()

@@ -57,3 +57,22 @@ def test_callable_lowering():
     assert log2 and np.allclose(tab, 0.1 * np.outer(np.arange(3), np.arange(3)))
     with pytest.raises(ValueError):
         T.lower_reward(lambda s, a, n: float(s[0] * s[1]), 3, 3, 3)
+
+
+def test_reward_callable_is_bound_to_the_env_shape():
+    """The host callable handed to agents must agree with the device table: with four levels, level 2 is an
+    interior level (role 1), not the polarised one -- which cannot be guessed from one (state, action) pair."""
+    f4 = T.right_polarizing.for_shape(4, 4)
+    tab4 = T.right_polarizing.table(4, 4)
+    assert f4((2,), (2,)) == tab4[2, 2] == 0.10            # role 1, action == level
+    assert T.right_polarizing((2,), (2,)) == 0.25          # three levels (the reference's shape): level 2 is polarised
+    assert f4((3,), (3,)) == tab4[3, 3] == 0.25
+    assert T.right_polarizing.for_shape(3, 3) is T.right_polarizing
+    for s in range(4):
+        for a in range(4):
+            assert f4((s, 0), (a, 0)) == tab4[s, a] + tab4[0, 0]
+
+
+def test_callable_depending_on_next_state_is_rejected():
+    with pytest.raises(ValueError, match="next_state"):
+        T.lower_reward(lambda s, a, n: float(sum(n)), 3, 3, 3)
