@@ -17,7 +17,7 @@ STAT_STEPS, STAT_UNSAFE, STAT_COUNT, STAT_TRUNCATED, STAT_REWARD_Q24 = range(5)
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_ACTION = 0, -1, -2, -3, -4
 POLICY_RANDOM, POLICY_TABLE = 0, 1
 
-EXPORTS = ["gc_abi_version", "gc_last_error", "gc_create", "gc_destroy", "gc_set_tables",
+EXPORTS = ["gc_abi_version", "gc_last_error", "gc_create", "gc_destroy", "gc_set_tables", "gc_set_final_obs",
            "gc_set_global_step", "gc_get_global_step", "gc_sync_global_step", "gc_launch_count", "gc_reset", "gc_step",
            "gc_bind_step", "gc_step_bound", "gc_step_many", "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode",
            "gc_decode", "gc_encode_mixed", "gc_decode_mixed", "gc_reset_packed", "gc_step_packed", "gc_bind_step_packed",
@@ -65,6 +65,7 @@ def load():
     L.gc_create.argtypes = [C.POINTER(GcConfig), C.POINTER(vp)]
     L.gc_destroy.argtypes = [vp]
     L.gc_set_tables.argtypes = [vp, C.POINTER(GcCellTables)]
+    L.gc_set_final_obs.argtypes = [vp, vp]
     L.gc_set_global_step.argtypes = [vp, i64]
     L.gc_get_global_step.argtypes = [vp]
     L.gc_get_global_step.restype = i64

@@ -87,6 +87,7 @@ struct gc_env {
     uint32_t *d_done;               // block-arrival counter of the step kernels
     uint2 *d_pair_lut;            // fast-path table (GC_PAIR_LUT_ENTRIES), device memory owned by the handle
     uint2 *d_packed_lut;          // the same rules in the packed layout's index order (gc_cell_packed.cu)
+    int8_t *final_state;          // gc_set_final_obs: optional extra output of every int8-layout step
     bool fast_ok;
     StepIO bound[GC_MAX_BINDINGS];  // gc_bind_step slots
     PackedIO bound_packed[GC_MAX_BINDINGS];   // gc_bind_step_packed slots
@@ -125,6 +126,7 @@ StepIO make_io(const gc_env *env, int64_t begin, int64_t count, const int8_t *ac
     io.actions = actions; io.state = state; io.t = t; io.reward = reward; io.index = index;
     io.terminated = terminated; io.truncated = truncated; io.unsafe = unsafe; io.count = count_out;
     io.se_row = se_row; io.replay = replay;
+    io.final_state = env->final_state;
     io.stats = reinterpret_cast<unsigned long long *>(stats);
     io.status = env->d_status;
     io.begin = begin; io.end = begin + count; io.ld = env->cfg.ld;
@@ -222,7 +224,7 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
         // Measured slower than the register-staged kernel (profiles/r01_tuning_log.md), so it is opt-in:
         // GC_B200_TMA=1 in the environment.
         static const bool use_tma = [] { const char *v = std::getenv("GC_B200_TMA"); return v && v[0] == '1'; }();
-        if (env->fast_ok && use_tma && mode == GC_RNG_NONE && !io.se_row && env->cfg.n_cells >= 8)
+        if (env->fast_ok && use_tma && mode == GC_RNG_NONE && !io.se_row && !io.final_state && env->cfg.n_cells >= 8)
             e = gc_launch_cell_tma_step(env->tab, io, env->d_pair_lut, env->n_sm, st);
         else if (env->fast_ok)
             e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, mode, env->n_sm, st);
@@ -390,6 +392,16 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
 
     tab.noise_thr_nz = tab.noise_thr != 0ull;
     tab.noise_thr_m1 = tab.noise_thr_nz ? static_cast<uint32_t>(tab.noise_thr - 1ull) : 0u;
+    {
+        // threshold = k8 * 2^24 + r24; a threshold of 2^32 (p >= 1) is k8 = 255, r24 = 2^24: a byte below 255
+        // fires, 255 ties and the tie always fires
+        uint32_t k8 = static_cast<uint32_t>(tab.noise_thr >> 24), r24 = static_cast<uint32_t>(tab.noise_thr & 0xFFFFFFull);
+        if (k8 > 255u) { k8 = 255u; r24 = 1u << 24; }
+        tab.noise_kk7 = (k8 & 0x7Fu) * 0x01010101u;
+        tab.noise_kmask = (k8 & 0x80u) ? 0xFFFFFFFFu : 0u;
+        tab.noise_kk = k8 * 0x01010101u;
+        tab.noise_r24 = r24;
+    }
 
     // ---- fast path: pair table (gc_cell_fast.cu) -------------------------------------------------
     // (a ragged index needs per-cell place values: generic kernel)
@@ -405,13 +417,22 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         GC_ON_DEVICE(env->cfg.device);
         if (!env->d_pair_lut) GC_CUDA(cudaMalloc(&env->d_pair_lut, sizeof(lut)));
         GC_CUDA(cudaMemcpy(env->d_pair_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
-        gc_build_packed_lut(t, C, S, A, noise, lut, tab.unsafe_spread);
+        gc_build_packed_lut(t, C, S, A, noise, lut);
         tab.init_packed = 0;
         for (int c = 0; c < C; ++c) tab.init_packed |= (uint32_t)(tab.init[c] & 3) << (2 * c);
         if (!env->d_packed_lut) GC_CUDA(cudaMalloc(&env->d_packed_lut, sizeof(lut)));
         GC_CUDA(cudaMemcpy(env->d_packed_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     }
     env->tables_set = true;
+    return GC_OK;
+}
+
+int gc_set_final_obs(gc_env *env, int8_t *final_state)
+{
+    if (int rc = check_env(env)) return rc;
+    env->final_state = final_state;
+    for (int i = 0; i < GC_MAX_BINDINGS; ++i)
+        if (env->bound_set[i] == 1) env->bound[i].final_state = final_state;
     return GC_OK;
 }
 

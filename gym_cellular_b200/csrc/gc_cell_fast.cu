@@ -34,11 +34,19 @@ namespace {
 #endif
 constexpr int pair_min_blocks(int c, int rng)
 {
-    if (rng == GC_RNG_PHILOX && c > 4) return 3;
-    // deterministic kernels whose 64-register build spills (the cell counts with a ragged or a single
-    // second group): measured faster with the 85-register budget of three blocks
-    // (profiles/r01_tuning_log.md, sweep over all cell counts)
-    if (rng == GC_RNG_NONE && ((c >= 4 && c <= 8) || c == 10 || c == 11)) return GC_PAIR_MINB < 3 ? GC_PAIR_MINB : 3;
+#ifdef GC_PAIR_MINB_ALL
+    return GC_PAIR_MINB_ALL;
+#endif
+    // Budgets chosen so that NO instantiation spills (cuobjdump --dump-resource-usage: 0 bytes of stack everywhere):
+    // cell counts whose second group is ragged or single (9-11) and the wide Philox / replay variants need
+    // more than the 85 registers of three blocks: two blocks (128 registers)
+    if (c >= 9 && c <= 11) return 2;
+    if (rng != GC_RNG_NONE && c > 8) return 2;
+    if (rng != GC_RNG_NONE && c > 4) return 3;
+    // deterministic kernels whose 64-register build spills: three blocks (85 registers) for 4, 8 and 13-15
+    // cells (measured faster than four, profiles/r01_tuning_log.md), two blocks for 5-7 cells
+    if (rng == GC_RNG_NONE && c >= 5 && c <= 7) return 2;
+    if (rng == GC_RNG_NONE && (c == 4 || c == 8 || (c >= 13 && c <= 15))) return GC_PAIR_MINB < 3 ? GC_PAIR_MINB : 3;
     return c < 4 ? GC_PAIR_MINB_NARROW : GC_PAIR_MINB;
 }
 
@@ -62,13 +70,17 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
                                          const uint2 *s_single, const uint8_t (*s_se)[GC_TBL], int c0,
                                          int64_t e0, int rem, uint32_t gid_lo, uint32_t gid_hi, uint32_t step_counter,
                                          const int (&tin)[kEPT], uint32_t keep, const uint32_t (&sw)[4],
-                                         const uint32_t (&aw)[4], EnvAcc &acc)
+                                         const uint32_t (&aw)[4], const uint32_t (&fire16)[kEPT], EnvAcc &acc)
 {
     // fb[e]: bit i = the noise draw of cell (c0 + i) of env e fired (the table ignores the bit where the
     // (level, action) pair consumes no draw).  The four random words are reduced to four bits at once so
     // that only one register per env stays live.
     uint32_t fb[kEPT] = {0, 0, 0, 0};
-    if (RNG == GC_RNG_PHILOX) {
+    if (RNG == GC_RNG_PHILOX && C > GC_NARROW_CELLS) {
+        // wide env: the fire bits of all cells were drawn from ONE Philox block per env (fire_bits_wide)
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) fb[e] = (fire16[e] >> c0) & 15u;
+    } else if (RNG == GC_RNG_PHILOX) {
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
             uint32_t w[4];
@@ -140,6 +152,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
         }
         const uint32_t out = (rows[i] & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c0 + i])) & ~keep);
         st_stream_u32(io.state + (c0 + i) * ld + e0, out);
+        if (io.final_state) st_stream_u32(io.final_state + (c0 + i) * ld + e0, rows[i]);
         q += out * tab.place4[i];
     }
     const uint32_t place = tab.place[c0];
@@ -243,25 +256,32 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
             for (int e = 0; e < kEPT; ++e)
                 if (tn[e] >= io.max_episode_steps) { tn[e] = 0; trunc_w |= 1u << (8 * e); keep &= ~(0xFFu << (8 * e)); }
         }
+        uint32_t fire16[kEPT] = {0, 0, 0, 0};
+        if (RNG == GC_RNG_PHILOX && C > GC_NARROW_CELLS) {
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                fire16[e] = fire_bits_wide<(C + 3) / 4>(tab, gid_lo | e, gid_hi, io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter,
+                                                        io.round_key);
+        }
         EnvAcc acc;
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.idx[e] = 0; }
         acc.sum01 = acc.sum23 = acc.or01 = acc.or23 = acc.s0w = acc.s1w = 0;
 
         if (NG == 0) {
-            do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
+            do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc);
         } else {
-            do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
+            do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc);
 #pragma unroll 1
             for (int g = 1; g < NG; ++g) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { sa[i] = sb[i]; aa[i] = ab[i]; }
                 if (g + 1 < NG) load_cells<4>(io, 4 * (g + 1), e0, sb, ab);
                 else if (R > 0) load_cells<R>(io, 4 * NG, e0, sb, ab);
-                do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, acc);
+                do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc);
             }
             if (R > 0)
-                do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sb, ab, acc);
+                do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sb, ab, fire16, acc);
         }
 
         // unsafe / count for the four envs at once (byte lanes): the count and the presence / flag bytes

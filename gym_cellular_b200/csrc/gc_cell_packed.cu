@@ -13,9 +13,11 @@
 //     x = (aw << 4 & 0xF0F0F0F0) | (sw & 0x0F0F0F0F)     byte k = index of pair 2k     (s nibble | a nibble << 4)
 //     y = (aw & 0xF0F0F0F0) | (sw >> 4 & 0x0F0F0F0F)     byte k = index of pair 2k + 1
 // and the next state is rebuilt by a funnel shift per pair (the entry carries the pair's next levels in its
-// top nibble: new = new << 4 | entry >> 28).  The info words of all pairs are simply ADDED: level counts (for
-// the 'unsafe' report of the cells j >= 2) and the polarised-cell count sit in carry-free 5-bit fields
-// (gc_tables.cu: gc_build_packed_lut).
+// top nibble: new = new << 4 | entry >> 28).  The info words of all pairs are simply ADDED: for each possible
+// next level k of cell 0, how many cells would report 'unsafe' (the side-effect report of the cells j >= 2 is
+// then one field extract by s'_0), and the polarised-cell count, in carry-free 5-bit fields (gc_tables.cu:
+// gc_build_packed_lut).  Per (env, pair) that is PRMT + IMAD (address), LDS.64, FADD, IADD, SHF: the integer
+// work is split between the two math pipes, which is what bounds the kernel once the bytes are this few.
 //
 // Shared-memory bank conflicts.  A warp's 32 random 64-bit table reads would serialise ~6-7-fold (measured on
 // the int8 kernel, profiles/r01_kernel_cfg4.md); with 25 bytes per env-step that, not HBM, would bound the
@@ -28,6 +30,22 @@
 namespace {
 
 constexpr int kPackThreads = 256;
+
+// (a & m) | (b & ~m) in one LOP3
+__device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
+// 64-bit shared-memory load from a 32-bit shared address (the tables are immutable after the staging barrier)
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 
 // resident blocks per SM the register budget is sized for
 #ifndef GC_PACKED_MINB
@@ -47,13 +65,14 @@ constexpr size_t packed_smem_bytes(int rng, bool big)
 // EXTRA: the launch also writes some of the optional outputs (separate tabular index for S < 4, final
 // state before the auto-reset, row-0 side-effect codes); the plain variant carries no registers for them.
 // the Philox and the optional-output variants carry ~16 more registers: budget of three blocks (85 registers)
-__host__ __device__ constexpr int packed_min_blocks(int rng, bool extra)
+__host__ __device__ constexpr int packed_min_blocks(int c, int rng, bool extra)
 {
-    return (rng != GC_RNG_NONE || extra) ? (GC_PACKED_MINB < 3 ? GC_PACKED_MINB : 3) : GC_PACKED_MINB;
+    // (15 cells: the 64-register build of the plain variant spills 8 bytes)
+    return (rng != GC_RNG_NONE || extra || c == 15) ? (GC_PACKED_MINB < 3 ? GC_PACKED_MINB : 3) : GC_PACKED_MINB;
 }
 
 template <int C, int RNG, bool EXTRA>
-__global__ void __launch_bounds__(kPackThreads, packed_min_blocks(RNG, EXTRA))
+__global__ void __launch_bounds__(kPackThreads, packed_min_blocks(C, RNG, EXTRA))
 cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ PackedIO io,
                    const uint2 *__restrict__ lut, const int REP_LOG2)
 {
@@ -65,7 +84,6 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
     uint2 *const s_pair = s_tab;
     uint2 *const s_single = s_tab + (N_PAIR << REP_LOG2);
     uint8_t (*const s_se)[GC_TBL] = reinterpret_cast<uint8_t (*)[GC_TBL]>(s_single + (N_SINGLE << REP_LOG2));
-    __shared__ uint32_t s_rows[4];
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const uint32_t REP = 1u << REP_LOG2;
@@ -77,7 +95,6 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
     for (int i = threadIdx.x; i < (N_SINGLE << REP_LOG2); i += kPackThreads) s_single[i] = lut[GC_PAIR_LUT_PAIRS + (i >> REP_LOG2)];
     if (EXTRA && io.se_row)
         for (int i = threadIdx.x; i < C * GC_TBL; i += kPackThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
-    if (threadIdx.x < 4) s_rows[threadIdx.x] = tab.unsafe_spread[threadIdx.x];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     pdl_launch_dependents();
     pdl_wait();
@@ -91,7 +108,11 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
     __syncthreads();
     const uint32_t step_now = step_counter_arrive(io, &s_ctr);
     const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? step_now : 0u;
+    // shared-memory byte addresses: entry ix of this lane's replica sits at ix * lut_mul + lane base
     const uint32_t rep = threadIdx.x & (REP - 1u);
+    const uint32_t lut_mul = 8u << REP_LOG2;
+    const uint32_t pair_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_pair)) + rep * 8u;
+    const uint32_t single_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_single)) + rep * 8u;
 
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
     long long st_reward = 0;
@@ -107,10 +128,10 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
             pa = ld_stream_v4(io.actions + e0 + stride);
             pt = ld_stream_v4(io.t + e0 + stride);
         }
-        uint32_t nstate[kEPT], fin[kEPT], idx[kEPT], flag[kEPT], sew[kEPT];
+        uint32_t nstate[kEPT], fin[kEPT], idx[kEPT], sew[kEPT];
+        uint32_t flags_w = 0;                          // flag bytes of the four envs
         float rew[kEPT];
         int tn[kEPT];
-        uint32_t trunc_n = 0, unsafe_n = 0, count_n = 0;
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
             const uint32_t sw = sw4[e], aw = aw4[e];
@@ -119,46 +140,48 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
             uint32_t fire = 0;
             if (RNG == GC_RNG_PHILOX) {
                 const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
-                const uint32_t thr = tab.noise_thr_m1;
-#pragma unroll
-                for (int g = 0; g < NGRP; ++g) {
+                if (C > GC_NARROW_CELLS) {             // wide env: one block, a byte per cell (fire_bits_wide)
+                    fire = fire_bits_wide<NGRP>(tab, gid_lo | e, gid_hi, ctr, io.round_key);
+                } else {
+                    const uint32_t thr = tab.noise_thr_m1;
                     uint32_t w[4];
-                    philox4x32_10(gid_lo | e, gid_hi, ctr, static_cast<uint32_t>(g), io.round_key, w);
-                    fire |= ((w[0] <= thr ? 1u : 0u) | (w[1] <= thr ? 2u : 0u) | (w[2] <= thr ? 4u : 0u) | (w[3] <= thr ? 8u : 0u)) << (4 * g);
+                    philox4x32_10(gid_lo | e, gid_hi, ctr, 0u, io.round_key, w);
+                    fire = (w[0] <= thr ? 1u : 0u) | (w[1] <= thr ? 2u : 0u) | (w[2] <= thr ? 4u : 0u) | (w[3] <= thr ? 8u : 0u);
                 }
             }
-            const uint32_t x = ((aw << 4) & 0xF0F0F0F0u) | (sw & 0x0F0F0F0Fu);
-            const uint32_t y = (aw & 0xF0F0F0F0u) | ((sw >> 4) & 0x0F0F0F0Fu);
-            uint32_t info[NP + (ODD ? 1 : 0)];
+            const uint32_t x = bitselect(aw << 4, sw, 0xF0F0F0F0u);       // (aw << 4 & M) | (sw & ~M)
+            const uint32_t y = bitselect(aw, sw >> 4, 0xF0F0F0F0u);
+            constexpr int NL = NP + (ODD ? 1 : 0);
+            uint32_t info[NL];
             float r = 0.f;
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
-                uint32_t ix = byte_of((i & 1) ? y : x, i >> 1);
+                uint32_t ix = prmt((i & 1) ? y : x, 0u, 0x4440u + (i >> 1));      // byte i/2: the pair's index
                 if (RNG != GC_RNG_NONE) ix |= ((fire >> (2 * i)) & 3u) << 8;
-                const uint2 ent = s_pair[(ix << REP_LOG2) | rep];
+                const uint2 ent = lds64(ix * lut_mul + pair_base);
                 r = (i == 0) ? __uint_as_float(ent.y) : r + __uint_as_float(ent.y);
                 info[i] = ent.x;
             }
             if (ODD) {
-                const uint32_t b = byte_of((NP & 1) ? y : x, NP >> 1);
+                const uint32_t b = prmt((NP & 1) ? y : x, 0u, 0x4440u + (NP >> 1));
                 uint32_t ix = (b & 3u) | ((b >> 2) & 12u);
                 if (RNG != GC_RNG_NONE) ix |= ((fire >> (2 * NP)) & 1u) << 4;
-                const uint2 ent = s_single[(ix << REP_LOG2) | rep];
+                const uint2 ent = lds64(ix * lut_mul + single_base);
                 r = (NP == 0) ? __uint_as_float(ent.y) : r + __uint_as_float(ent.y);
                 info[NP] = ent.x;
             }
-            constexpr int NL = NP + (ODD ? 1 : 0);
             uint32_t ns = 0, acc = 0;
 #pragma unroll
             for (int i = NL - 1; i >= 0; --i) {
                 ns = __funnelshift_l(info[i], ns, 4);              // ns << 4 | next nibble of lookup i
                 acc += info[i];
             }
-            // 'unsafe': the pair (cell 0, cell 1) flag, or some level present among the cells j >= 2 that the
-            // side-effect table of s'_0 marks unsafe; count: polarised cells of the next state
-            const uint32_t lv = acc - info[0];                     // level counts of the cells j >= 2
-            const uint32_t nz = (((lv & 0x7BDEFu) + 0x7BDEFu) | lv) & 0x84210u;
-            const uint32_t uns = (((info[0] >> 25) & 1u) | ((nz & s_rows[ns & 3u]) ? 1u : 0u));
+            // 'unsafe': the pair (cell 0, cell 1) flag, or some cell j >= 2 whose level the side-effect table of
+            // s'_0 marks unsafe (field s'_0 of the summed info words of the lookups >= 1);
+            // count: polarised cells of the next state
+            const uint32_t lv = acc - info[0];
+            const uint32_t uns2 = ((lv >> (5u * (ns & 3u))) & 31u) ? 1u : 0u;
+            const uint32_t uns = ((info[0] >> 25) & 1u) | uns2;
             const uint32_t cnt = (acc >> 20) & 31u;
             uint32_t se_code = 0;
             if (EXTRA && io.se_row) {
@@ -172,14 +195,19 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
                     se_code |= static_cast<uint32_t>(s_se[j][s0n * GC_LVL_PAD + sp]) << (2 * j);
                 }
             }
-            int t1 = tin[e] + 1;
-            uint32_t tr = 0, out = ns;
-            if (io.max_episode_steps > 0 && t1 >= io.max_episode_steps) { t1 = 0; tr = 1u; out = tab.init_packed; }
-            nstate[e] = out; tn[e] = t1;
+            nstate[e] = ns; tn[e] = tin[e] + 1;
             if (EXTRA) { fin[e] = ns; sew[e] = se_code; }
             rew[e] = r;
-            flag[e] = uns | (tr << 1) | (cnt << 2);
-            if (e < rem) { trunc_n += tr; unsafe_n += uns; count_n += cnt; }
+            flags_w |= (uns | (cnt << 2)) << (8 * e);
+        }
+        if (io.max_episode_steps > 0) {                // time limit (uniform branch: the reference has none)
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                if (tn[e] >= io.max_episode_steps) { tn[e] = 0; nstate[e] = tab.init_packed; flags_w |= 2u << (8 * e); }
+        }
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) {
+            const uint32_t out = nstate[e];
             // tabular index of the returned state: the packed word itself for four levels
             if (EXTRA) {
                 uint32_t ix = out;
@@ -196,12 +224,19 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
 #pragma unroll
         for (int e = 0; e < kEPT; ++e)
             if (e < rem) st_reward += __float2int_rn(rout[e] * 16777216.0f);
-        st_steps += rem; st_unsafe += unsafe_n; st_count += count_n; st_trunc += trunc_n;
+        {
+            // statistics of the four envs from the flag word (envs beyond the range masked out)
+            const uint32_t fw = flags_w & valid_bytes(rem);
+            st_steps += rem;
+            st_unsafe += __popc(fw & 0x01010101u);
+            st_trunc += __popc(fw & 0x02020202u);
+            st_count = add_bytes((fw >> 2) & 0x1F1F1F1Fu, st_count);
+        }
         st_stream_v4(io.state + e0, make_int4(nstate[0], nstate[1], nstate[2], nstate[3]));
         st_stream_v4(io.t + e0, make_int4(tn[0], tn[1], tn[2], tn[3]));
         st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
                                                __float_as_int(rout[2]), __float_as_int(rout[3])));
-        st_stream_u32(io.flags + e0, flag[0] | (flag[1] << 8) | (flag[2] << 16) | (flag[3] << 24));
+        st_stream_u32(io.flags + e0, flags_w);
         if (EXTRA) {
             if (io.index) st_stream_v4(io.index + e0, make_int4(idx[0], idx[1], idx[2], idx[3]));
             if (io.final_state) st_stream_v4(io.final_state + e0, make_int4(fin[0], fin[1], fin[2], fin[3]));

@@ -45,12 +45,20 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const int64_t ld = io.ld;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
+    // Work partition: the 4-env words of the launch are cut into gridDim.x CONTIGUOUS chunks of (almost)
+    // equal length, one per block, and a block strides over its chunk.  With a grid-stride loop a launch of
+    // 1.7 waves (2^20 envs: 512 blocks of work on 296 resident blocks) leaves the first 216 blocks with two
+    // iterations and the rest with one, and the SMs that host two two-iteration blocks finish last; equal
+    // chunks give every SM the same number of words.
+    const int64_t n_words = (io.end - io.begin + kEPT - 1) / kEPT;
+    const int64_t w_lo = n_words * blockIdx.x / gridDim.x, w_hi = n_words * (blockIdx.x + 1) / gridDim.x;
+    const int64_t e_end = (io.begin + w_hi * kEPT < io.end) ? io.begin + w_hi * kEPT : io.end;
+    constexpr int64_t stride = static_cast<int64_t>(kGridThreads) * kEPT;
     // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
     // reads 32 bytes per word, so without the prefetch too few bytes are in flight per SM to cover the
     // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).  The first word's inputs are
     // requested before the table is staged, so that the two latencies overlap.
-    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kGridThreads + threadIdx.x) * kEPT;
+    int64_t e0 = io.begin + (w_lo + threadIdx.x) * kEPT;
     // the immutable table is requested first (possibly while the previous step kernel of the stream is
     // still running: gc_device.cuh, programmatic dependent launch), then the first word's inputs, then
     // the table is stored to shared memory, so that the two latencies overlap
@@ -68,7 +76,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     pdl_wait();
     uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;
     int4 p_t = make_int4(0, 0, 0, 0);
-    if (e0 < io.end) {
+    if (e0 < e_end) {
         p_s0 = ld_stream_u32(io.state + e0); p_s1 = ld_stream_u32(io.state + ld + e0);
         p_a0 = ld_stream_u32(io.actions + e0); p_a1 = ld_stream_u32(io.actions + ld + e0);
         p_t = ld_stream_v4(io.t + e0);
@@ -87,13 +95,13 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
 
     const uint32_t step_counter = step_counter_arrive(io, &s_ctr);
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
-    for (; e0 < io.end; e0 += stride) {
-        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
+    for (; e0 < e_end; e0 += stride) {
+        const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
         const uint32_t s0w = p_s0, s1w = p_s1;
         uint32_t a0w = p_a0, a1w = p_a1;
         const int4 t4 = p_t;
-        if (e0 + stride < io.end) {
+        if (e0 + stride < e_end) {
             const int64_t en = e0 + stride;
             p_s0 = ld_stream_u32(io.state + en); p_s1 = ld_stream_u32(io.state + ld + en);
             p_a0 = ld_stream_u32(io.actions + en); p_a1 = ld_stream_u32(io.actions + ld + en);
@@ -194,6 +202,10 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         uint32_t row0 = prmt(u, v, 0x5410), row1 = prmt(u, v, 0x7632);         // next codes, byte 0 / byte 1
         uint32_t trunc_w = 0;
         int tout[kEPT] = {tin[0] + 1, tin[1] + 1, tin[2] + 1, tin[3] + 1};
+        if (io.final_state) {                                                // final observation: before the auto-reset
+            st_stream_u32(io.final_state + e0, row0);
+            st_stream_u32(io.final_state + ld + e0, row1);
+        }
         if (io.max_episode_steps > 0) {
             uint32_t keep = 0xFFFFFFFFu;
 #pragma unroll

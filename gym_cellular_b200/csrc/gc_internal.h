@@ -8,6 +8,11 @@
 #define GC_LVL_PAD 8                       // tables are indexed [s * GC_LVL_PAD + a]
 #define GC_TBL (GC_LVL_PAD * GC_LVL_PAD)   // 64 entries
 
+// Cellular noise draws: envs of up to GC_NARROW_CELLS cells take one 32-bit Philox word per cell (one block
+// per env); wider envs take one byte per cell of one block plus 24 lazily drawn bits (gc_device.cuh)
+#define GC_NARROW_CELLS 4
+#define GC_NOISE_LOW_STREAM 0x20000000u   // Philox stream of the low 24 bits of cell c's draw: GC_NOISE_LOW_STREAM + c
+
 // RNG source of a launch
 enum { GC_RNG_NONE = 0, GC_RNG_PHILOX = 1, GC_RNG_REPLAY = 2 };
 
@@ -20,6 +25,7 @@ struct StepIO {
     uint32_t     *index;
     uint8_t      *terminated, *truncated, *unsafe, *count;
     int8_t       *se_row;       // optional
+    int8_t       *final_state;  // optional, [C][ld]: next state BEFORE the time-limit auto-reset (final observation)
     const double *replay;       // optional, [n][slots]
     unsigned long long *stats;  // optional, int64[GC_N_STATS]
     unsigned long long *status; // handle-owned status word
@@ -93,9 +99,14 @@ struct CellTables {
     unsigned long long noise_thr;    // draw fires iff word < noise_thr  (word*2^-32 < p)
     uint32_t noise_thr_m1;           // noise_thr - 1 (32-bit compare: fires iff thr != 0 and word <= thr - 1)
     uint32_t noise_thr_nz;
+    // wide envs (more than GC_NARROW_CELLS cells): one BYTE of one Philox block per cell, the low 24 bits of the
+    // draw only on a tie of that byte with the threshold's top byte (gc_device.cuh: fire_bits_wide)
+    uint32_t noise_kk7;              // (k8 & 0x7F) * 0x01010101, k8 = top byte of the threshold
+    uint32_t noise_kmask;            // all ones iff k8 >= 0x80
+    uint32_t noise_kk;               // k8 * 0x01010101
+    uint32_t noise_r24;              // low 24 bits of the threshold: on a tie the draw fires iff its low 24 bits < r24
     double   noise_prob;             // for the replay path (compares doubles like the reference)
     // packed layout (gc_cell_packed.cu)
-    uint32_t unsafe_spread[4];       // [s0']: bit 5x+4 set iff SE[j>=2][s0'][x] == unsafe (level counts live in 5-bit fields)
     uint32_t init_packed;            // initial state, 2 bits per cell
 };
 
@@ -131,7 +142,7 @@ cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, co
 cudaError_t gc_launch_cell_tma_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
                                     cudaStream_t stream);
 // packed layout: lut = GC_PAIR_LUT_ENTRIES entries in the packed index order (gc_build_packed_lut)
-void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut, uint32_t *unsafe_spread);
+void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut);
 cudaError_t gc_launch_cell_packed_step(const CellTables &tab, const PackedIO &io, const uint2 *lut, bool noise,
                                        int n_sm, cudaStream_t stream);
 cudaError_t gc_launch_reset_packed(uint32_t init_packed, uint32_t init_index, const uint8_t *mask, uint32_t *state,

@@ -67,6 +67,14 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         uint32_t idx[kEPT] = {0, 0, 0, 0};
         uint32_t unsafe_w = 0, count_w = 0, row0 = 0;        // row0: next levels of cell 0 (byte lanes)
         uint32_t rnd[kEPT][4];
+        uint32_t fire16[kEPT] = {0, 0, 0, 0};
+        const bool wide = C > GC_NARROW_CELLS;
+        if (RNG == GC_RNG_PHILOX && wide) {                   // wide env: one Philox block per env (fire_bits_wide)
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                fire16[e] = fire_bits_wide<4>(tab, gid_lo | e, gid_hi, io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter,
+                                              io.round_key);
+        }
 
 #pragma unroll 1
         for (int c = 0; c < C; ++c) {
@@ -75,7 +83,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                 sn = ld_stream_u32(io.state + (c + 1) * ld + e0);
                 an = ld_stream_u32(io.actions + (c + 1) * ld + e0);
             }
-            if (RNG == GC_RNG_PHILOX && (c & 3) == 0) {
+            if (RNG == GC_RNG_PHILOX && !wide && (c & 3) == 0) {
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e) {
                     const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
@@ -90,7 +98,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                 bool fire = false;
                 if (RNG == GC_RNG_PHILOX) {
                     const uint32_t word = (c & 3) == 0 ? rnd[e][0] : (c & 3) == 1 ? rnd[e][1] : (c & 3) == 2 ? rnd[e][2] : rnd[e][3];
-                    fire = (ent.x & 0x100u) && tab.noise_thr_nz && word <= tab.noise_thr_m1;
+                    fire = (ent.x & 0x100u) && tab.noise_thr_nz && (wide ? ((fire16[e] >> c) & 1u) != 0u : word <= tab.noise_thr_m1);
                 } else if (RNG == GC_RNG_REPLAY) {
                     if (e < rem && (ent.x & 0x100u)) fire = io.replay[(e0 + e) * C + c] < tab.noise_prob;
                 }
@@ -123,6 +131,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
             }
             const uint32_t out = (row & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c])) & ~keep);
             st_stream_u32(io.state + c * ld + e0, out);
+            if (io.final_state) st_stream_u32(io.final_state + c * ld + e0, row);
             const uint32_t place = tab.place[c];
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) idx[e] += byte_of(out, e) * place;

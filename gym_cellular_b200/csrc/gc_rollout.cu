@@ -126,16 +126,24 @@ cell_rollout_kernel(const __grid_constant__ CellTables tab, const __grid_constan
             uint32_t add[kEPT] = {0, 0, 0, 0}, orr[kEPT] = {0, 0, 0, 0}, first[kEPT] = {0, 0, 0, 0};
             uint32_t rows[C];
             uint32_t rnd[kEPT][4];
+            uint32_t fire16[kEPT] = {0, 0, 0, 0};
+            constexpr bool WIDE = C > GC_NARROW_CELLS;        // wide env: one Philox block per env (fire_bits_wide)
+            if (NOISE && WIDE && tab.noise_thr_nz) {
+#pragma unroll
+                for (int e = 0; e < kEPT; ++e)
+                    fire16[e] = fire_bits_wide<(C + 3) / 4>(tab, gid_lo | e, gid_hi, T[e], io.round_key);
+            }
 #pragma unroll
             for (int kk = 0; kk < NPAIR + (ODD ? 1 : 0); ++kk) {
                 const int c = 2 * kk, d = 2 * kk + 1;
                 const bool pair = kk < NPAIR;
-                if (NOISE && (c & 3) == 0) {
+                if (NOISE && !WIDE && (c & 3) == 0) {
 #pragma unroll
                     for (int e = 0; e < kEPT; ++e)
                         philox4x32_10(gid_lo | e, gid_hi, T[e], static_cast<uint32_t>(c >> 2), io.round_key, rnd[e]);
                 }
                 auto fire = [&](int e, int cell) -> uint32_t {
+                    if (WIDE) return (fire16[e] >> cell) & 1u;
                     return (NOISE && tab.noise_thr_nz && rnd[e][cell & 3] <= tab.noise_thr_m1) ? 1u : 0u;
                 };
                 uint32_t inf[kEPT];

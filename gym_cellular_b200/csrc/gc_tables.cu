@@ -100,7 +100,8 @@ void gc_build_pair_lut(const gc_cell_tables *t, int C, int S, int A, bool noise,
 // the packed words deliver the digits and with the info word laid out for whole-word accumulation.
 //   pair index   p = (s_c | s_d << 2) | (a_c | a_d << 2) << 4 | fire_c << 8 | fire_d << 9
 //   single index p = s | a << 2 | fire << 4                       (entries GC_PAIR_LUT_PAIRS ..)
-//   .x  bits  0-4 / 5-9 / 10-14 / 15-19   how many of the entry's next levels equal level 0 / 1 / 2 / 3
+//   .x  bits  5k .. 5k+4 (k = 0..3)   how many of the entry's next levels x have SE[j >= 2][k][x] == 'unsafe',
+//                   i.e. would be reported unsafe if cell 0 ended at level k             (:157-212)
 //       bits 20-24  how many of them count towards the incidence          (cells3states3actions3.py:159-162)
 //       bit  25     row-0 entries 0 and 1 of the side-effects matrix hold 'unsafe' for (s'_c, s'_d)
 //                   (meaningful for the pair (cell 0, cell 1); single entry: for a 1-cell env)   (:157-212)
@@ -108,7 +109,7 @@ void gc_build_pair_lut(const gc_cell_tables *t, int C, int S, int A, bool noise,
 //   .y  reward contribution (float)                                                              (:9-45)
 // The sum of the .x words of an env's entries has no carries between the fields (<= 16 cells), and the
 // nibble sits on top so that whatever its sum carries out of is discarded.
-void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut, uint32_t *unsafe_spread)
+void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut)
 {
     auto ok = [&](int s, int a) { return s < S && a < A; };
     auto nxt = [&](int s, int a, int fire) {
@@ -122,7 +123,13 @@ void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool nois
         return (double)t->reward[s * A + a];
     };
     auto se = [&](int j, int s0, int sp) { return (int)t->side_effects[((size_t)j * S + s0) * S + sp]; };
-    auto info = [&](int n) { return (1u << (5 * n)) | (t->counted[n] ? (1u << 20) : 0u); };
+    auto info = [&](int n) {
+        uint32_t w = t->counted[n] ? (1u << 20) : 0u;
+        if (C >= 3)
+            for (int k = 0; k < S; ++k)
+                if (se(2, k, n) == 2) w |= 1u << (5 * k);
+        return w;
+    };
     for (int p = 0; p < GC_PAIR_LUT_PAIRS; ++p) {
         const int sc = p & 3, sd = (p >> 2) & 3, ac = (p >> 4) & 3, ad = (p >> 6) & 3;
         const int fc = (p >> 8) & 1, fd = (p >> 9) & 1;
@@ -138,11 +145,5 @@ void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool nois
         lut[GC_PAIR_LUT_PAIRS + p].x = info(n) | (uns0 << 25) | ((uint32_t)n << 28);
         const float f = (float)rw(s, a, (p >> 4) & 1);
         std::memcpy(&lut[GC_PAIR_LUT_PAIRS + p].y, &f, sizeof(f));
-    }
-    for (int s0 = 0; s0 < 4; ++s0) {
-        unsafe_spread[s0] = 0;
-        if (C >= 3 && s0 < S)
-            for (int x = 0; x < S; ++x)
-                if (se(2, s0, x) == 2) unsafe_spread[s0] |= 1u << (5 * x + 4);
     }
 }

@@ -52,8 +52,7 @@ class PackedCellularVectorEnv(CellularVectorEnv):
     views, so a device-path step() is exactly one kernel launch.
     """
 
-    def __init__(self, *args, emit_side_effects=False, emit_final_obs=False, **kwargs):
-        self.emit_final_obs = bool(emit_final_obs)
+    def __init__(self, *args, emit_side_effects=False, **kwargs):
         kwargs.setdefault("kind", "cellular")
         if kwargs["kind"] != "cellular":
             raise ValueError("the packed layout covers the cellular (polarisation) family")

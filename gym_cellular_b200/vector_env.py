@@ -56,6 +56,9 @@ class CellularVectorEnv(gym.vector.VectorEnv):
     rng_episodic    RNG counter = episode step, i.e. every episode replays the same noise, which is
                     what the reference's re-seeding reset() does (cells3resetVdeadlock.py:131)
     max_episode_steps   None/0 = never truncate (reference); > 0 = time limit with fused auto-reset
+    emit_final_obs  also write the observation BEFORE a time-limit auto-reset: infos['final_obs'] (valid where
+                    infos['_final_obs'], i.e. truncated) and infos['final_info'] -- gymnasium's SAME_STEP
+                    convention; the reference itself never ends an episode (gym_cellular/__init__.py:7)
     env_id_offset   global id of env 0: Philox streams are keyed by global id, so a batch sharded
                     over ranks reproduces the single-device results env by env
     """
@@ -68,7 +71,8 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                  difficulty="easy", reward_func=None, stochastic=False, deadlock=False,
                  noise_prob=0.1, dispersal_prob=0.01, env_seed=0, rng_episodic=None,
                  max_episode_steps=None, device=None, env_id_offset=0, emit_side_effects=True,
-                 collect_stats=True, host_chunk_envs=1 << 20, cell_tables=None, force_generic_kernel=False):
+                 collect_stats=True, host_chunk_envs=1 << 20, cell_tables=None, force_generic_kernel=False,
+                 emit_final_obs=False, cell_radix=None):
         self._lib = _lib.load()                      # raises ImportError when the .so is missing
         if not torch.cuda.is_available():
             raise RuntimeError("CellularVectorEnv needs a CUDA device: there is no CPU fallback")
@@ -100,6 +104,10 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         self.env_seed = int(env_seed)
         self.env_id_offset = int(env_id_offset)
         self.emit_side_effects = bool(emit_side_effects)
+        self.emit_final_obs = bool(emit_final_obs)
+        # ragged state space: levels of each cell for the tabular index (the reference's codec takes one space
+        # per cell, generalized_space_transformations.py:1-12); the moves must keep cell c below cell_radix[c]
+        self.cell_radix = None if cell_radix is None else [int(r) for r in cell_radix]
         self.host_chunk_envs = int(host_chunk_envs)
         self.ld = _round_up(self.num_envs, 16)
 
@@ -168,6 +176,9 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         self._count = z(ld, dtype=torch.uint8)
         self._se_row = z(Cn, ld, dtype=torch.int8) if self.emit_side_effects else None
         self._stats = z(_lib.N_STATS, dtype=torch.int64) if self._collect_stats else None
+        self._final = z(Cn, ld, dtype=torch.int8) if self.emit_final_obs else None
+        if self._final is not None:          # an extra output of every following step of the handle
+            _lib.check(self._lib.gc_set_final_obs(self._h, _ptr(self._final)))
 
     def _spaces(self):
         if self._batched_spaces is None:
@@ -216,7 +227,10 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                 np.ascontiguousarray(se, np.int8),
                 np.ascontiguousarray(counted, np.uint8),
                 np.zeros(Cn, np.int8),
-                None if reward_noisy is None else np.ascontiguousarray(reward_noisy, np.float32)]
+                None if reward_noisy is None else np.ascontiguousarray(reward_noisy, np.float32),
+                None if self.cell_radix is None else np.ascontiguousarray(self.cell_radix, np.int32)]
+        if self.cell_radix is not None and len(self.cell_radix) != Cn:
+            raise ValueError("cell_radix needs one entry per cell")
         t = _lib.GcCellTables(*[None if a is None else a.ctypes.data for a in keep])
         _lib.check(self._lib.gc_set_tables(self._h, C.byref(t)))
         self.side_effect_table = se
@@ -350,6 +364,8 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                 self._se_row[0].fill_(tables.SAFE)
             else:
                 self._se_row.fill_(tables.SAFE)
+        if self._final is not None:
+            self._final.copy_(self._state)
         # the global step (RNG counter of the non-episodic kinds: grid world, DeepExplorationDebug) is NOT
         # rewound: the reference never re-seeds these envs (grid_world.py:97-104), every episode draws
         # fresh numbers.  The episodic kinds count from the per-env episode step, which reset() zeroes.
@@ -560,6 +576,13 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         self._v_infos[key] = self._index[:n]
         if self._se_row is not None:
             self._v_infos["side_effects"] = self._se_row[:, :n]
+        if self._final is not None:
+            # gymnasium SAME_STEP auto-reset: the observation the episode ended with, valid where `_final_obs`;
+            # reward / unsafe / count / side_effects of the returned step already describe that final step
+            self._v_infos["final_obs"] = tuple(self._final[c, :n] for c in range(self.n_cells))
+            self._v_infos["_final_obs"] = self._v_trunc
+            self._v_infos["final_info"] = _FinalInfo(self)
+            self._v_infos["_final_info"] = self._v_trunc
 
     def _obs_device(self):
         return self._v_obs
@@ -635,6 +658,28 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         if "se_row" in h:
             infos["side_effects"] = h["se_row"][:, :n]
         return obs, h["reward"][:n], h["terminated"][:n].view(np.bool_), h["truncated"][:n].view(np.bool_), infos
+
+
+class _FinalInfo(dict):
+    """infos['final_info']: the info of the step an episode ended with.  `unsafe`, `count` and `side_effects`
+    are the step's own (they always describe the step taken); `tabular_state` is the index of the final
+    observation, encoded on demand."""
+
+    def __init__(self, env):
+        super().__init__()
+        self._env = env
+
+    def __missing__(self, key):
+        env = self._env
+        if key == "tabular_state":
+            radix = 20 if env.kind == "gridworld" else env.n_states
+            out = torch.empty(env.ld, dtype=torch.int32, device=env.device)
+            _lib.check(env._lib.gc_encode(env.device.index, env.num_envs, env.ld, env.n_cells, radix,
+                                          _ptr(env._final), _ptr(out), env._stream()))
+            return out[:env.num_envs].to(torch.int64) & 0xFFFFFFFF
+        if key in ("unsafe", "count", "side_effects"):
+            return env._v_infos[key]
+        raise KeyError(key)
 
 
 def make_vector_env(env_id, num_envs, layout="int8", **kwargs):

@@ -137,6 +137,13 @@ int gc_create(const gc_config *cfg, gc_env **out);
 int gc_destroy(gc_env *env);
 int gc_set_tables(gc_env *env, const gc_cell_tables *tables);   /* cellular family only */
 
+/* Final observation (gymnasium's SAME_STEP auto-reset convention; the reference never ends an episode,
+ * gym_cellular/__init__.py:7, so this belongs to the time limit added here): when set, every following
+ * int8-layout step of the handle (gc_step, bound steps, gc_step_host) also writes the next state BEFORE the
+ * auto-reset to final_state, int8 [C][ld] device memory owned by the caller; it equals `state` wherever
+ * truncated == 0.  NULL switches it off.  Not part of the 3C + 20 algorithmic bytes (+C when on). */
+int gc_set_final_obs(gc_env *env, int8_t *final_state);
+
 /* Global step counter used as the RNG counter when GC_F_RNG_EPISODIC is off.  It lives in device
  * memory: a gc_step over the whole shard reads it in the kernel and the kernel advances it, so a
  * gc_step captured into a CUDA graph keeps drawing fresh numbers on every replay.  The host keeps a

@@ -59,7 +59,11 @@ typedef struct {
  * device RNG layer is new (the reference uses numpy's global MT19937); this is its CPU twin.
  * word(env, t, w) = philox(key = seed, ctr = (env_lo, env_hi, t, w / 4))[w % 4]
  * and the uniform handed to the reference-style comparison is u = word * 2^-32 (exact).
- * Cellular family: draw slot c (cell c) uses word c of the env's own stream.
+ * Cellular family, envs of up to NARROW_CELLS = 4 cells: draw slot c (cell c) uses word c of the env's own
+ * stream.  Wider envs: ONE block per env and step, byte c of it (byte j of word i = cell 4 i + j) is the top
+ * byte of cell c's 32-bit draw and the low 24 bits are word 0 >> 8 of philox(key, ctr = (env_lo, env_hi, t,
+ * NOISE_LOW_STREAM + c)); u = (top byte << 24 | low 24) * 2^-32.  (The device looks at the low bits only
+ * when the top byte ties with the threshold's: the comparison u < p is decided by the top byte otherwise.)
  * Grid world: the trigger draw of env g is word (g % 4) of the block shared by the four envs
  * g/4*4 .. g/4*4+3:  w = philox(key, ctr = ((g/4)_lo, (g/4)_hi, t, 0))[g % 4]  (one Philox block per
  * four env-steps), u = w * 2^-32.  When the trigger fires (w < p * 2^32) the binary draws that
@@ -68,6 +72,8 @@ typedef struct {
  * tree_positions == 0 in the reference).
  */
 static const int GW_SLOT_BIT[6] = {-1, 0, 3, 1, 4, 2};
+#define NARROW_CELLS 4
+#define NOISE_LOW_STREAM 0x20000000u
 
 static void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
 {
@@ -115,6 +121,20 @@ static double draw_uniform(draw_src *d, int slot)
         uint32_t word = w[d->env_id & 3];
         if (slot == 0) return (double)word * (1.0 / 4294967296.0);              /* trigger */
         return ((word >> GW_SLOT_BIT[slot]) & 1u) ? 0.75 : 0.25;                /* randint(2) = floor(u * 2) */
+    }
+    if (d->cfg->n_cells > NARROW_CELLS) {
+        /* wide env: byte `slot` of block 0 is the top byte of the draw, the low 24 bits come from word 0 of the
+         * block of stream NOISE_LOW_STREAM + slot (the device draws them only when the top byte ties) */
+        if (d->cached_block != 0) {
+            uint32_t ctr[4] = {(uint32_t)d->env_id, (uint32_t)(d->env_id >> 32), d->t, 0u};
+            philox4x32_10(ctr, key, d->words);
+            d->cached_block = 0;
+        }
+        uint32_t top = (d->words[slot >> 2] >> (8 * (slot & 3))) & 0xFFu;
+        uint32_t ctr2[4] = {(uint32_t)d->env_id, (uint32_t)(d->env_id >> 32), d->t, NOISE_LOW_STREAM + (uint32_t)slot};
+        uint32_t v[4];
+        philox4x32_10(ctr2, key, v);
+        return (double)((top << 24) | (v[0] >> 8)) * (1.0 / 4294967296.0);
     }
     int blk = slot >> 2;
     if (blk != d->cached_block) {

@@ -37,6 +37,6 @@ def test_native_arm_line():
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["bytes_per_env_step"] == 29.0 and r["algorithmic_bytes_per_launch"] == 29 * 65536
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] == 3 * 65536 and e["d2h_bytes_per_step"] == 13 * 65536 and 0 < e["value"] < d["value"]
+    assert e["h2d_bytes_per_step"] == 4 * 65536 and e["d2h_bytes_per_step"] == 13 * 65536 and 0 < e["value"] < d["value"]
     assert d["clocks"]["sm_max_mhz"] and not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
     assert d["cpu_baseline"]["kind"] == "port" and d["config"]["workload"] == "cfg2"

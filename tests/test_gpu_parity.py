@@ -912,3 +912,118 @@ def test_gridworld_staged_table_on_second_device(B, O):
         env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=4, device=d)
         env.step_device(torch.from_numpy(a).to(d))
         assert (host(env.state) == ora.state).all() and (host(env._reward[:n]) == ora.reward).all()
+
+
+def test_mixed_radix_codec_on_device(B, O, golden_pol):
+    """gc_encode_mixed / gc_decode_mixed: the reference's codec with its per-cell space list (arbitrary min
+    and length per cell), against the reference's own outputs (codec_ragged_* fixtures) and the oracle."""
+    g = golden_pol
+    lens, mins, cells = g["codec_ragged_lens"], g["codec_ragged_mins"], g["codec_ragged_cells"]
+    spaces = [range(int(m), int(m) + int(l)) for m, l in zip(mins, lens)]
+    n = len(cells)                                             # row i of the fixture encodes to i
+    idx = B.encode_mixed(dev(cells.T.astype(np.int8)), spaces)
+    assert (host(idx) == np.arange(n)).all()
+    back = B.decode_mixed(torch.arange(n, device="cuda"), spaces)
+    assert (host(back).T == cells).all()
+    for i in (0, 17, n - 1):
+        assert O.encode_mixed_radix(cells[i], mins, lens) == int(idx[i]) and (O.decode_mixed_radix(i, mins, lens) == host(back)[:, i]).all()
+    # 16 cells x 4 levels through the mixed entry points: the full unsigned 32-bit range
+    sp16 = [range(0, 4)] * 16
+    c16, t16 = g["codec_c16_cells"], g["codec_c16_tab"]
+    assert (host(B.encode_mixed(dev(c16.T.copy()), sp16)).astype(np.uint64) == t16).all()
+    assert (host(B.decode_mixed(dev(t16.astype(np.int64)), sp16)).T == c16).all()
+    # a large ragged batch against the host codec
+    rng = np.random.default_rng(0)
+    spaces = [range(-1, 2), range(0, 5), range(3, 5), range(-4, 3), range(0, 1), range(10, 17)]
+    cells = np.stack([rng.integers(min(s), max(s) + 1, 10007) for s in spaces]).astype(np.int8)
+    want = np.array([B.generalized_cellular2tabular([int(x) for x in cells[:, i]], spaces) for i in range(0, 10007, 97)])
+    got = B.encode_mixed(dev(cells), spaces)
+    assert (host(got)[::97] == want).all()
+    assert (host(B.decode_mixed(got, spaces)) == cells).all()
+    from gym_cellular_b200 import _lib
+    with pytest.raises(_lib.GcError, match="32-bit"):
+        B.encode_mixed(dev(np.zeros((9, 16), np.int8)), [range(0, 16)] * 9)
+
+
+def test_ragged_state_space_index_in_step(B, O):
+    """Per-cell level counts (gc_cell_tables.radix): the step's tabular index is the reference's mixed-radix
+    index of a ragged space list, everything else is unchanged."""
+    n, radix = 5003, [2, 4, 3, 4, 2]
+    spaces = [range(0, r) for r in radix]
+    env = B.CellularVectorEnv(num_envs=n, n_cells=5, n_states=4, cell_radix=radix, max_episode_steps=6)
+    ora = O.OracleEnv(n_envs=n, n_cells=5, n_states=4, max_episode_steps=6)
+    rng = np.random.default_rng(4)
+    for t in range(10):
+        a = np.stack([rng.integers(0, r, n) for r in radix]).astype(np.int8)      # actions keep cell c below radix[c]
+        env.step_device(dev(a))
+        ora.step(a)
+        st = host(env.state)
+        assert (st == ora.state).all() and (st < np.array(radix)[:, None]).all()
+        want = host(B.encode_mixed(env.state, spaces))
+        assert (host(env.tabular_state()) == want).all()
+        assert int(want[7]) == O.encode_mixed_radix(st[:, 7], np.zeros(5, np.int64), np.array(radix, np.int64))
+        np.testing.assert_allclose(host(env._reward[:n]), ora.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+
+
+@pytest.mark.parametrize("kind", ["cellular3", "cellular16", "generic", "gridworld"])
+def test_final_observation_int8_layout(B, O, kind):
+    """emit_final_obs: for every truncated env `final_obs` is the oracle's next state BEFORE the auto-reset
+    (an oracle without time limit, re-synchronised every step); elsewhere it equals the observation."""
+    n = 6007
+    gw = kind == "gridworld"
+    C, S = {"cellular3": (3, 3), "cellular16": (16, 4), "generic": (4, 6), "gridworld": (2, 20)}[kind]
+    if gw:
+        env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=3, max_episode_steps=4, emit_final_obs=True, dispersal_prob=0.1)
+        mk = lambda lim: O.OracleEnv(kind="gridworld", n_envs=n, seed=3, max_episode_steps=lim, dispersal_prob=0.1)
+    else:
+        env = B.CellularVectorEnv(num_envs=n, n_cells=C, n_states=S, stochastic=True, env_seed=3, max_episode_steps=4,
+                                  emit_final_obs=True)
+        mk = lambda lim: O.OracleEnv(n_envs=n, n_cells=C, n_states=S, noise=True, rng_episodic=True, seed=3,
+                                     max_episode_steps=lim, reward="nonlinear_rp")
+    lim, free = mk(4), mk(0)
+    rng = np.random.default_rng(6)
+    seen = 0
+    for t in range(9):
+        if gw:
+            a = np.full((2, n), 4, np.int8)
+            a[rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+        else:
+            a = rng.integers(0, S, size=(C, n)).astype(np.int8)
+        free.state[:], free.t[:], free.global_step = lim.state, lim.t, lim.global_step
+        obs, rew, term, trunc, infos = env.step(dev(a))
+        free.step(a)
+        lim.step(a)
+        assert_matches_oracle(env, lim, check_se=False)
+        fin = host(torch.stack(infos["final_obs"]))
+        assert (fin == free.state).all()
+        tr = host(infos["_final_obs"])
+        assert (tr == lim.truncated.astype(bool)).all()
+        assert (fin[:, ~tr] == lim.state[:, ~tr]).all()
+        assert (host(infos["final_info"]["tabular_state"]) == free.index).all()
+        seen += int(tr.sum())
+    assert seen == 2 * n
+
+
+def test_step_many_int8_layout(B, O):
+    """gc_step_many on the int8 layout: 19 steps over a ring of 8 bound action buffers in one foreign call,
+    grid world (global-step RNG counter, read from device memory by every launch)."""
+    n = 20011
+    env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=5, max_episode_steps=7, dispersal_prob=0.1)
+    ora = O.OracleEnv(kind="gridworld", n_envs=n, seed=5, max_episode_steps=7, dispersal_prob=0.1)
+    rng = np.random.default_rng(11)
+    acts = []
+    for _ in range(8):
+        a = np.full((2, n), 4, np.int8)
+        a[rng.integers(0, 2, n), np.arange(n)] = rng.integers(0, 4, n)
+        acts.append(a)
+    ring = []
+    for a in acts:
+        t = torch.zeros(2, env.ld, dtype=torch.int8, device="cuda")
+        t[:, :n] = dev(a)
+        ring.append(t)
+    slots = [env._bind(t) for t in ring]
+    env.step_many(slots, 19)
+    for i in range(19):
+        ora.step(acts[i % 8])
+    assert_matches_oracle(env, ora, check_se=False)
+    assert env.sync_step_counter() == 19

@@ -101,3 +101,33 @@ def test_install_alias_keeps_reference_imports_working():
     env = dict(__import__("os").environ, PYTHONPATH=__import__("conftest").REPO)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0 and "alias ok" in out.stdout, out.stderr[-800:]
+
+
+def test_async_vector_env_stand_in():
+    """The AsyncVectorEnv look-alike (worker processes, one pipe round trip per step) used as the CPU
+    baseline harness: batched results equal stepping the same envs in-process."""
+    from gym_cellular_b200._gym import gym
+    from oracle.pyport import PolarisationEnv
+    n, k = 6, 2
+    fns = [lambda: PolarisationEnv(3, 3) for _ in range(n)]
+    kw = {"envs_per_worker": k} if gym.vector.AsyncVectorEnv.__module__.startswith("gymnasium.vector.async_vector_env") and \
+        "compat" in gym.__file__ else {}
+    venv = gym.vector.AsyncVectorEnv(fns, shared_memory=False, **kw)
+    try:
+        if kw:
+            assert venv.num_workers == n // k
+        obs, _ = venv.reset()
+        assert len(obs) == 3 and all((o == 0).all() for o in obs)
+        local = [PolarisationEnv(3, 3) for _ in range(n)]
+        for e in local:
+            e.reset()
+        rng = np.random.default_rng(1)
+        for _ in range(12):
+            acts = tuple(rng.integers(0, 3, n) for _ in range(3))
+            obs, rew, term, trunc, infos = venv.step(acts)
+            want = [e.step(tuple(int(a[i]) for a in acts)) for i, e in enumerate(local)]
+            assert (np.stack(obs).T == np.array([w[0] for w in want])).all()
+            assert (rew == np.array([w[1] for w in want])).all() and not term.any() and not trunc.any()
+            assert (infos["per_env"][3]["side_effects"] == want[3][4]["side_effects"]).all()
+    finally:
+        venv.close()
