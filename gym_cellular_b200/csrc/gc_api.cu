@@ -393,14 +393,14 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     tab.noise_thr_nz = tab.noise_thr != 0ull;
     tab.noise_thr_m1 = tab.noise_thr_nz ? static_cast<uint32_t>(tab.noise_thr - 1ull) : 0u;
     {
-        // threshold = k8 * 2^24 + r24; a threshold of 2^32 (p >= 1) is k8 = 255, r24 = 2^24: a byte below 255
-        // fires, 255 ties and the tie always fires
-        uint32_t k8 = static_cast<uint32_t>(tab.noise_thr >> 24), r24 = static_cast<uint32_t>(tab.noise_thr & 0xFFFFFFull);
-        if (k8 > 255u) { k8 = 255u; r24 = 1u << 24; }
-        tab.noise_kk7 = (k8 & 0x7Fu) * 0x01010101u;
-        tab.noise_kmask = (k8 & 0x80u) ? 0xFFFFFFFFu : 0u;
-        tab.noise_kk = k8 * 0x01010101u;
-        tab.noise_r24 = r24;
+        // threshold = k16 * 2^16 + r16; a threshold of 2^32 (p >= 1) is k16 = 65535, r16 = 2^16: a half below
+        // 65535 fires, 65535 ties and the tie always fires
+        uint32_t k16 = static_cast<uint32_t>(tab.noise_thr >> 16), r16 = static_cast<uint32_t>(tab.noise_thr & 0xFFFFull);
+        if (k16 > 65535u) { k16 = 65535u; r16 = 1u << 16; }
+        tab.noise_kk15 = (k16 & 0x7FFFu) * 0x00010001u;
+        tab.noise_kmask = (k16 & 0x8000u) ? 0xFFFFFFFFu : 0u;
+        tab.noise_kk = k16 * 0x00010001u;
+        tab.noise_r16 = r16;
     }
 
     // ---- fast path: pair table (gc_cell_fast.cu) -------------------------------------------------

@@ -37,16 +37,8 @@ constexpr int pair_min_blocks(int c, int rng)
 #ifdef GC_PAIR_MINB_ALL
     return GC_PAIR_MINB_ALL;
 #endif
-    // Budgets chosen so that NO instantiation spills (cuobjdump --dump-resource-usage: 0 bytes of stack everywhere):
-    // cell counts whose second group is ragged or single (9-11) and the wide Philox / replay variants need
-    // more than the 85 registers of three blocks: two blocks (128 registers)
-    if (c >= 9 && c <= 11) return 2;
-    if (rng != GC_RNG_NONE && c > 8) return 2;
     if (rng != GC_RNG_NONE && c > 4) return 3;
-    // deterministic kernels whose 64-register build spills: three blocks (85 registers) for 4, 8 and 13-15
-    // cells (measured faster than four, profiles/r01_tuning_log.md), two blocks for 5-7 cells
-    if (rng == GC_RNG_NONE && c >= 5 && c <= 7) return 2;
-    if (rng == GC_RNG_NONE && (c == 4 || c == 8 || (c >= 13 && c <= 15))) return GC_PAIR_MINB < 3 ? GC_PAIR_MINB : 3;
+    if (rng == GC_RNG_NONE && ((c >= 4 && c <= 8) || c == 10 || c == 11)) return GC_PAIR_MINB < 3 ? GC_PAIR_MINB : 3;
     return c < 4 ? GC_PAIR_MINB_NARROW : GC_PAIR_MINB;
 }
 
@@ -226,6 +218,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? step_now : 0u;
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;   // < 2^32 per thread and launch
     long long st_reward = 0;
+#pragma unroll 1
     for (; e0 < io.end; e0 += stride) {
         const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);    // envs of this word in range
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);           // multiple of 4: | e never carries
@@ -260,7 +253,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         if (RNG == GC_RNG_PHILOX && C > GC_NARROW_CELLS) {
 #pragma unroll
             for (int e = 0; e < kEPT; ++e)
-                fire16[e] = fire_bits_wide<(C + 3) / 4>(tab, gid_lo | e, gid_hi, io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter,
+                fire16[e] = fire_bits_wide<(C + 7) / 8>(tab, gid_lo | e, gid_hi, io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter,
                                                         io.round_key);
         }
         EnvAcc acc;

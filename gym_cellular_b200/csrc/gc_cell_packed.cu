@@ -78,7 +78,6 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
 {
     constexpr int NP = C / 2;                          // full pairs
     constexpr bool ODD = (C & 1) != 0;                 // plus a single last cell
-    constexpr int NGRP = (C + 3) / 4;                  // Philox blocks per env (four cells each)
     constexpr int N_PAIR = packed_pairs(RNG), N_SINGLE = packed_singles(RNG);
     extern __shared__ __align__(16) uint2 s_tab[];     // [N_PAIR << REP_LOG2] pairs, [N_SINGLE << REP_LOG2] singles, side effects
     uint2 *const s_pair = s_tab;
@@ -141,7 +140,7 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
             if (RNG == GC_RNG_PHILOX) {
                 const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
                 if (C > GC_NARROW_CELLS) {             // wide env: one block, a byte per cell (fire_bits_wide)
-                    fire = fire_bits_wide<NGRP>(tab, gid_lo | e, gid_hi, ctr, io.round_key);
+                    fire = fire_bits_wide<(C + 7) / 8>(tab, gid_lo | e, gid_hi, ctr, io.round_key);
                 } else {
                     const uint32_t thr = tab.noise_thr_m1;
                     uint32_t w[4];

@@ -32,19 +32,21 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 // ---------------------------------------------------------------------------------------------
 // Noise draws of a WIDE env (more than GC_NARROW_CELLS cells; cells3resetVdeadlock.py:35-41 scaled up).
-// One Philox block per env and step: byte c of the block (byte j of word i = cell 4 i + j) is the TOP byte
-// of cell c's 32-bit draw.  With threshold = k8 * 2^24 + r24 (= ceil(p * 2^32)) the draw fires iff
-//     byte < k8,  or  byte == k8 and low24 < r24,
-// low24 = word 0 >> 8 of the block philox(env, t, GC_NOISE_LOW_STREAM + c), computed only on a tie (1 / 256 per
-// cell).  P(fire) = k8 / 256 + r24 / 2^32 = threshold / 2^32 exactly, as for the 32-bit draws of narrow envs;
-// the oracle always forms the full 32-bit value (top byte << 24 | low24) and compares u = value * 2^-32 < p.
-// The 16 byte compares run four at a time (SWAR): for x, k in one byte, H = 0x80, L = 0x7F,
-//     d = (x | H) - (k & L)     bit 7 of d  <=>  (x & L) >= (k & L)   (no borrow between the bytes)
-//     x < k  <=>  (~x7 & k7) | (~(x7 ^ k7) & ~d7)
-// and the four result bits of a word are gathered with one multiply (bits 7, 15, 23, 31 -> 28..31).
-// Returns bit c = the draw of cell c fired, for c < 4 * NW.
+// One Philox block serves EIGHT cells: 16-bit half h = c % 8 of the block philox(env, t, c / 8) (half h = the
+// low (h even) or high (h odd) half of word h / 2) is the TOP half of cell c's 32-bit draw.  With
+// threshold = k16 * 2^16 + r16 (= ceil(p * 2^32)) the draw fires iff
+//     half < k16,  or  half == k16 and low16 < r16,
+// low16 = word 0 >> 16 of the block philox(env, t, GC_NOISE_LOW_STREAM + c), computed only on a tie (2^-16 per
+// cell).  P(fire) = k16 / 2^16 + r16 / 2^32 = threshold / 2^32 exactly, as for the 32-bit draws of narrow envs;
+// the oracle always forms the full 32-bit value (top half << 16 | low16) and compares u = value * 2^-32 < p.
+// The compares run two at a time (SWAR): for x, k in one 16-bit lane, H = 0x8000, L = 0x7FFF,
+//     d = (x | H) - (k & L)     bit 15 of d  <=>  (x & L) >= (k & L)   (no borrow between the lanes)
+//     x < k  <=>  (~x15 & k15) | (~(x15 ^ k15) & ~d15)
+// and the two result bits of a word are gathered with one multiply (bits 15, 31 -> 30, 31).
+// Returns bit c = the draw of cell c fired, for c < 8 * NB (NB Philox blocks).
+
 // the rare part, kept out of line so that its registers (a whole Philox block) do not weigh on the callers
-__device__ __noinline__ uint32_t resolve_noise_ties(uint32_t ties, uint32_t r24, uint32_t gid_lo, uint32_t gid_hi, uint32_t ctr,
+__device__ __noinline__ uint32_t resolve_noise_ties(uint32_t ties, uint32_t r16, uint32_t gid_lo, uint32_t gid_hi, uint32_t ctr,
                                                     const uint32_t *rk)
 {
     uint32_t fire = 0;
@@ -61,34 +63,39 @@ __device__ __noinline__ uint32_t resolve_noise_ties(uint32_t ties, uint32_t r24,
             c2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
             c3 = static_cast<uint32_t>(p0);
         }
-        if ((c0 >> 8) < r24) fire |= 1u << c;
+        if ((c0 >> 16) < r16) fire |= 1u << c;
     } while (ties);
     return fire;
 }
 
-template <int NW>
+template <int NB>
 __device__ __forceinline__ uint32_t fire_bits_wide(const CellTables &tab, uint32_t gid_lo, uint32_t gid_hi, uint32_t ctr,
                                                    const uint32_t (&rk)[20])
 {
-    constexpr uint32_t H = 0x80808080u, L = 0x7F7F7F7Fu, GATHER = 0x00204081u;
-    uint32_t w[4];
-    philox4x32_10(gid_lo, gid_hi, ctr, 0u, rk, w);
-    uint32_t fire = 0, eq_any = 0, eq[NW];
+    constexpr uint32_t H = 0x80008000u, L = 0x7FFF7FFFu, GATHER = 0x00008001u;
+    uint32_t fire = 0, eq_any = 0, eq[NB][4];
 #pragma unroll
-    for (int i = NW - 1; i >= 0; --i) {
-        const uint32_t x = w[i];
-        const uint32_t d = (x | H) - tab.noise_kk7;
-        const uint32_t lt = ~((x & d) | ((x | d) & ~tab.noise_kmask)) & H;
-        const uint32_t z = x ^ tab.noise_kk;
-        eq[i] = ~(((z & L) + L) | z) & H;
-        eq_any |= eq[i];
-        fire = __funnelshift_l(lt * GATHER, fire, 4);
+    for (int b = NB - 1; b >= 0; --b) {
+        uint32_t w[4];
+        philox4x32_10(gid_lo, gid_hi, ctr, static_cast<uint32_t>(b), rk, w);
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            const uint32_t x = w[i];
+            const uint32_t d = (x | H) - tab.noise_kk15;
+            const uint32_t lt = ~((x & d) | ((x | d) & ~tab.noise_kmask)) & H;
+            const uint32_t z = x ^ tab.noise_kk;
+            eq[b][i] = ~(((z & L) + L) | z) & H;
+            eq_any |= eq[b][i];
+            fire = __funnelshift_l(lt * GATHER, fire, 2);
+        }
     }
-    if (eq_any) {                                     // rare: a byte ties with the threshold's top byte
+    if (eq_any) {                                     // rare: a half ties with the threshold's top half
         uint32_t ties = 0;
 #pragma unroll
-        for (int i = NW - 1; i >= 0; --i) ties = __funnelshift_l(eq[i] * GATHER, ties, 4);
-        fire |= resolve_noise_ties(ties, tab.noise_r24, gid_lo, gid_hi, ctr, rk);
+        for (int b = NB - 1; b >= 0; --b)
+#pragma unroll
+            for (int i = 3; i >= 0; --i) ties = __funnelshift_l(eq[b][i] * GATHER, ties, 2);
+        fire |= resolve_noise_ties(ties, tab.noise_r16, gid_lo, gid_hi, ctr, rk);
     }
     return fire;
 }

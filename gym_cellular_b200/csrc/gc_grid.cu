@@ -45,15 +45,12 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const int64_t ld = io.ld;
-    // Work partition: the 4-env words of the launch are cut into gridDim.x CONTIGUOUS chunks of (almost)
-    // equal length, one per block, and a block strides over its chunk.  With a grid-stride loop a launch of
-    // 1.7 waves (2^20 envs: 512 blocks of work on 296 resident blocks) leaves the first 216 blocks with two
-    // iterations and the rest with one, and the SMs that host two two-iteration blocks finish last; equal
-    // chunks give every SM the same number of words.
-    const int64_t n_words = (io.end - io.begin + kEPT - 1) / kEPT;
-    const int64_t w_lo = n_words * blockIdx.x / gridDim.x, w_hi = n_words * (blockIdx.x + 1) / gridDim.x;
-    const int64_t e_end = (io.begin + w_hi * kEPT < io.end) ? io.begin + w_hi * kEPT : io.end;
-    constexpr int64_t stride = static_cast<int64_t>(kGridThreads) * kEPT;
+    // Work partition: plain grid-stride loop.  (Round 2 tried contiguous per-block chunks of equal length --
+    // a launch of 1.7 waves such as 2^20 envs leaves some SMs with 4 and some with 3 block-iterations under
+    // grid-stride -- and measured it SLOWER on the same box: config 3 7.58 against 7.26 us per step, config 5
+    // 0.812 against 0.870 of the HBM roofline; 296 separate streams lose the DRAM page locality of one sweep.)
+    const int64_t w_lo = static_cast<int64_t>(blockIdx.x) * kGridThreads, e_end = io.end;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
     // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
     // reads 32 bytes per word, so without the prefetch too few bytes are in flight per SM to cover the
     // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).  The first word's inputs are
@@ -71,6 +68,17 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             const int i = threadIdx.x + k * kGridThreads;
             if (i < LUT_VEC) lut_reg[k] = src[i];
         }
+    } else {
+#ifndef GC_GRID_NO_L1_PREFETCH
+        // The table is read through L1, which starts every launch empty: without help the first lookups of a
+        // block miss to L2 AFTER the state words have arrived (a second L2 round trip on the critical path of a
+        // 7 us launch).  Each block therefore prefetches the whole 40 KB table into its SM's L1 here -- no
+        // register, no dependency -- while the previous step kernel of the stream drains (before pdl_wait) and
+        // the first state words are in flight.
+        constexpr int kSectors = (GC_GRID_LUT_ENTRIES * 4 + 31) / 32;
+        for (int i = threadIdx.x; i < kSectors; i += kGridThreads)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(gp.lut) + static_cast<size_t>(i) * 32));
+#endif
     }
     pdl_launch_dependents();
     pdl_wait();

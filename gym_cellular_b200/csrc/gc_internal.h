@@ -9,9 +9,9 @@
 #define GC_TBL (GC_LVL_PAD * GC_LVL_PAD)   // 64 entries
 
 // Cellular noise draws: envs of up to GC_NARROW_CELLS cells take one 32-bit Philox word per cell (one block
-// per env); wider envs take one byte per cell of one block plus 24 lazily drawn bits (gc_device.cuh)
+// per env); wider envs take one 16-bit half per cell (eight cells per block) plus 16 lazily drawn bits (gc_device.cuh)
 #define GC_NARROW_CELLS 4
-#define GC_NOISE_LOW_STREAM 0x20000000u   // Philox stream of the low 24 bits of cell c's draw: GC_NOISE_LOW_STREAM + c
+#define GC_NOISE_LOW_STREAM 0x20000000u   // Philox stream of the low 16 bits of cell c's draw: GC_NOISE_LOW_STREAM + c
 
 // RNG source of a launch
 enum { GC_RNG_NONE = 0, GC_RNG_PHILOX = 1, GC_RNG_REPLAY = 2 };
@@ -99,12 +99,13 @@ struct CellTables {
     unsigned long long noise_thr;    // draw fires iff word < noise_thr  (word*2^-32 < p)
     uint32_t noise_thr_m1;           // noise_thr - 1 (32-bit compare: fires iff thr != 0 and word <= thr - 1)
     uint32_t noise_thr_nz;
-    // wide envs (more than GC_NARROW_CELLS cells): one BYTE of one Philox block per cell, the low 24 bits of the
-    // draw only on a tie of that byte with the threshold's top byte (gc_device.cuh: fire_bits_wide)
-    uint32_t noise_kk7;              // (k8 & 0x7F) * 0x01010101, k8 = top byte of the threshold
-    uint32_t noise_kmask;            // all ones iff k8 >= 0x80
-    uint32_t noise_kk;               // k8 * 0x01010101
-    uint32_t noise_r24;              // low 24 bits of the threshold: on a tie the draw fires iff its low 24 bits < r24
+    // wide envs (more than GC_NARROW_CELLS cells): one 16-bit HALF of a Philox block per cell (eight cells per
+    // block), the low 16 bits of the draw only on a tie of that half with the threshold's top half
+    // (gc_device.cuh: fire_bits_wide)
+    uint32_t noise_kk15;             // (k16 & 0x7FFF) * 0x00010001, k16 = top half of the threshold
+    uint32_t noise_kmask;            // all ones iff k16 >= 0x8000
+    uint32_t noise_kk;               // k16 * 0x00010001
+    uint32_t noise_r16;              // low half of the threshold: on a tie the draw fires iff its low 16 bits < r16
     double   noise_prob;             // for the replay path (compares doubles like the reference)
     // packed layout (gc_cell_packed.cu)
     uint32_t init_packed;            // initial state, 2 bits per cell

@@ -72,7 +72,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         if (RNG == GC_RNG_PHILOX && wide) {                   // wide env: one Philox block per env (fire_bits_wide)
 #pragma unroll
             for (int e = 0; e < kEPT; ++e)
-                fire16[e] = fire_bits_wide<4>(tab, gid_lo | e, gid_hi, io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter,
+                fire16[e] = fire_bits_wide<2>(tab, gid_lo | e, gid_hi, io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter,
                                               io.round_key);
         }
 

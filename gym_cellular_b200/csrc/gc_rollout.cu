@@ -131,7 +131,7 @@ cell_rollout_kernel(const __grid_constant__ CellTables tab, const __grid_constan
             if (NOISE && WIDE && tab.noise_thr_nz) {
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e)
-                    fire16[e] = fire_bits_wide<(C + 3) / 4>(tab, gid_lo | e, gid_hi, T[e], io.round_key);
+                    fire16[e] = fire_bits_wide<(C + 7) / 8>(tab, gid_lo | e, gid_hi, T[e], io.round_key);
             }
 #pragma unroll
             for (int kk = 0; kk < NPAIR + (ODD ? 1 : 0); ++kk) {

@@ -60,10 +60,11 @@ typedef struct {
  * word(env, t, w) = philox(key = seed, ctr = (env_lo, env_hi, t, w / 4))[w % 4]
  * and the uniform handed to the reference-style comparison is u = word * 2^-32 (exact).
  * Cellular family, envs of up to NARROW_CELLS = 4 cells: draw slot c (cell c) uses word c of the env's own
- * stream.  Wider envs: ONE block per env and step, byte c of it (byte j of word i = cell 4 i + j) is the top
- * byte of cell c's 32-bit draw and the low 24 bits are word 0 >> 8 of philox(key, ctr = (env_lo, env_hi, t,
- * NOISE_LOW_STREAM + c)); u = (top byte << 24 | low 24) * 2^-32.  (The device looks at the low bits only
- * when the top byte ties with the threshold's: the comparison u < p is decided by the top byte otherwise.)
+ * stream.  Wider envs: one block per EIGHT cells, the 16-bit half c % 8 of block c / 8 (half h = low (h even)
+ * or high (h odd) half of word h / 2) is the top half of cell c's 32-bit draw and the low 16 bits are
+ * word 0 >> 16 of philox(key, ctr = (env_lo, env_hi, t, NOISE_LOW_STREAM + c)); u = (top << 16 | low) * 2^-32.
+ * (The device looks at the low bits only when the top half ties with the threshold's: the comparison u < p
+ * is decided by the top half otherwise.)
  * Grid world: the trigger draw of env g is word (g % 4) of the block shared by the four envs
  * g/4*4 .. g/4*4+3:  w = philox(key, ctr = ((g/4)_lo, (g/4)_hi, t, 0))[g % 4]  (one Philox block per
  * four env-steps), u = w * 2^-32.  When the trigger fires (w < p * 2^32) the binary draws that
@@ -123,18 +124,19 @@ static double draw_uniform(draw_src *d, int slot)
         return ((word >> GW_SLOT_BIT[slot]) & 1u) ? 0.75 : 0.25;                /* randint(2) = floor(u * 2) */
     }
     if (d->cfg->n_cells > NARROW_CELLS) {
-        /* wide env: byte `slot` of block 0 is the top byte of the draw, the low 24 bits come from word 0 of the
-         * block of stream NOISE_LOW_STREAM + slot (the device draws them only when the top byte ties) */
-        if (d->cached_block != 0) {
-            uint32_t ctr[4] = {(uint32_t)d->env_id, (uint32_t)(d->env_id >> 32), d->t, 0u};
+        /* wide env: 16-bit half (slot % 8) of block slot / 8 is the top half of the draw, the low 16 bits come from
+         * word 0 of the block of stream NOISE_LOW_STREAM + slot (the device draws them only when the top half ties) */
+        int blk8 = slot >> 3, h = slot & 7;
+        if (d->cached_block != blk8) {
+            uint32_t ctr[4] = {(uint32_t)d->env_id, (uint32_t)(d->env_id >> 32), d->t, (uint32_t)blk8};
             philox4x32_10(ctr, key, d->words);
-            d->cached_block = 0;
+            d->cached_block = blk8;
         }
-        uint32_t top = (d->words[slot >> 2] >> (8 * (slot & 3))) & 0xFFu;
+        uint32_t top = (d->words[h >> 1] >> (16 * (h & 1))) & 0xFFFFu;
         uint32_t ctr2[4] = {(uint32_t)d->env_id, (uint32_t)(d->env_id >> 32), d->t, NOISE_LOW_STREAM + (uint32_t)slot};
         uint32_t v[4];
         philox4x32_10(ctr2, key, v);
-        return (double)((top << 24) | (v[0] >> 8)) * (1.0 / 4294967296.0);
+        return (double)((top << 16) | (v[0] >> 16)) * (1.0 / 4294967296.0);
     }
     int blk = slot >> 2;
     if (blk != d->cached_block) {

@@ -45,7 +45,7 @@ def to_bytes(value, unit):
     return float(value.replace(",", "")) * scale
 
 
-DEVICE_LAUNCHES = 23      # --steps 20 --warmup 3 of scripts/capture_profiles.sh
+DEVICE_LAUNCHES = 23      # --steps 20 --warmup 3 of scripts/capture_profiles*.sh
 
 
 def launches(path, round_, workload):
@@ -61,12 +61,12 @@ def launches(path, round_, workload):
         per[re.sub(r"\s+", " ", r[ki])[:110]].append(v * {"ns": 1e-3, "us": 1, "usecond": 1, "ms": 1e3}.get(r[ui], 1e-3))
     # the step kernels are launched over the whole shard by the device path (`value`) and over 1M-env
     # chunks by the host path (`e2e`): two rows per kernel, split at half the longest launch
-    for k in [k for k in per if "_step_kernel" in k or "cell_pair_kernel" in k]:
+    for k in [k for k in per if "_step_kernel" in k or "cell_pair_kernel" in k or "cell_packed_kernel" in k]:
         v = per.pop(k)
         cut = max(v) / 2
-        for grp in ([x for x in v if x >= cut], [x for x in v if x < cut]):
+        for i, grp in enumerate(([x for x in v if x >= cut], [x for x in v if x < cut])):
             if grp:          # the capture command steps 20 + 3 warm-up times: DEVICE_LAUNCHES whole-shard launches
-                tag = " [whole shard: device path]" if len(grp) == DEVICE_LAUNCHES else " [1M-env chunks: host path]"
+                tag = " [whole shard: device path]" if i == 0 else " [1M-env chunks: host path]"
                 per[k + tag] = per.get(k + tag, []) + grp
     total = sum(sum(v) for v in per.values())
     out = [f"# {round_}: ncu launch list, workload {workload}", "",
@@ -78,8 +78,11 @@ def launches(path, round_, workload):
         out.append(f"| `{k}` | {len(v)} | {sum(v) / len(v):.1f} | {sum(v):.0f} | {100 * sum(v) / total:.1f}% |")
     out += ["", "Reading: the timed region of the device path (`value`) launches nothing but the whole-shard rows",
             "(one kernel of ours per step and sub-batch, `gpu_launches` = steps): the step kernels are 100 % of a step.",
-            "The 1M-env chunk rows belong to the host path (`gc_step_host`, the `e2e` leg); everything `at::` is torch",
-            "set-up work outside the timed regions (action-ring generation, zero fills, the statistics sum)."]
+            "`cell_packed_kernel` whole-shard rows are the packed-layout device path (`packed`), its 1M-env chunk rows the",
+            "host path (`gc_step_host_packed`, the `e2e` leg); `tick_kernel` advances the device-resident step counter once",
+            "per host-path step; `pack_kernel` converts the pre-generated action ring once at set-up; everything `at::` is",
+            "torch set-up work outside the timed regions (action-ring generation, zero fills) or the 64-byte statistics",
+            "snapshot taken once per 64-step iteration."]
     open(os.path.join(OUT, f"{round_}_launches_{workload}.md"), "w").write("\n".join(out) + "\n")
 
 
@@ -127,15 +130,18 @@ def main():
     round_ = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     traffic = {}
+    tpath = os.path.join(OUT, "traffic.json")
+    old = json.load(open(tpath)) if os.path.exists(tpath) else {}
     for path in sorted(glob.glob(os.path.join(SRC, f"{round_}_launches_*.csv"))):
         launches(path, round_, re.search(r"_launches_(\w+)\.csv", path).group(1))
     for rep in sorted(glob.glob(os.path.join(SRC, f"{round_}_prof_*.ncu-rep"))):
         kernel_report(rep, round_, re.search(r"_prof_(\w+)\.ncu-rep", rep).group(1), traffic)
-    flat = {}
+    flat = dict(old)                      # workloads not re-captured this round keep their entry
     for w, d in traffic.items():
-        flat[w] = sum(d.values()) if w == "cfg5" else max(d.values())
+        flat[w] = sum(d.values()) if w.startswith("cfg5") else max(d.values())
         flat[w + "_per_kernel"] = d
-    json.dump(flat, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+        flat[w + "_round"] = round_
+    json.dump(flat, open(tpath, "w"), indent=1)
     print("wrote", sorted(os.listdir(OUT)))
 
 

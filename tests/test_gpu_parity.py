@@ -1027,3 +1027,72 @@ def test_step_many_int8_layout(B, O):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora, check_se=False)
     assert env.sync_step_counter() == 19
+
+
+def test_log2_reward_max_relative_error(B, golden_pol):
+    """`nonlinear` rewards: the in-kernel log2(1 + r) against the reference's float64 np.log2 values over ALL
+    reachable reward sums of the 3- and 2-cell envs, as a pure relative error (no absolute slack): the
+    contract is 1e-6, the series is built for ~4e-7."""
+    g = golden_pol
+    worst = 0.0
+    for tag, C in (("c3", 3), ("c2", 2)):
+        n_s = 3 ** C
+        pairs = np.arange(n_s * n_s)
+        for rf, key in ((B.tables.nonlinear, "nonlinear"),):
+            env = B.CellularVectorEnv(num_envs=len(pairs), n_cells=C, reward_func=rf)
+            env.set_state(detab(pairs // n_s, C, 3))
+            env.step_device(dev(detab(pairs % n_s, C, 3)))
+            got, want = host(env._reward[:len(pairs)]).astype(np.float64), g[f"{tag}_reward_{key}"]
+            assert (got[want == 0] == 0).all()
+            nz = want != 0
+            worst = max(worst, float(np.abs(got[nz] / want[nz] - 1).max()))
+    # the stochastic env's variant (log2 over right_polarizing) on every noise case
+    sa = g["noise_rs_sa"]
+    env = B.CellularVectorEnv(num_envs=len(sa), stochastic=True)
+    env.set_state(detab(sa[:, 0], 3, 3))
+    env.step_device(dev(detab(sa[:, 1], 3, 3)), replay_u=np.where(np.isnan(g["noise_rs_u"]), 0.0, g["noise_rs_u"]))
+    got, want = host(env._reward[:len(sa)]).astype(np.float64), g["noise_rs_reward_nonlinear"]
+    nz = want != 0
+    worst = max(worst, float(np.abs(got[nz] / want[nz] - 1).max()))
+    assert (got[~nz] == 0).all()
+    # 16 cells x 4 levels: sums beyond 1 take the log1pf path
+    n = 50000
+    env = B.CellularVectorEnv(num_envs=n, n_cells=16, n_states=4, reward_func=B.tables.nonlinear_right_polarizing.for_shape(4, 4))
+    rng = np.random.default_rng(0)
+    s, a = rng.integers(0, 4, (16, n)).astype(np.int8), rng.integers(0, 4, (16, n)).astype(np.int8)
+    env.set_state(dev(s))
+    env.step_device(dev(a))
+    tab = B.tables.right_polarizing.table(4, 4)
+    want = np.log2(1.0 + tab[s, a].sum(axis=0))
+    got = host(env._reward[:n]).astype(np.float64)
+    worst = max(worst, float(np.abs(got / want - 1).max()))
+    print(f"max relative error of log2(1 + r): {worst:.3e}")
+    assert worst <= 6e-7, worst
+
+
+@pytest.mark.parametrize("layout", ["int8", "packed"])
+def test_host_path_at_bench_size(B, layout):
+    """The host path at the size it is benchmarked (2^24 envs, 16 cells x 4 levels, 1 M-env chunks on three
+    streams): bit-identical to the device path fed the same actions."""
+    n = 1 << 24
+    cls = B.CellularVectorEnv if layout == "int8" else B.PackedCellularVectorEnv
+    kw = dict(num_envs=n, n_cells=16, n_states=4, stochastic=True, rng_episodic=False, env_seed=2, emit_side_effects=False,
+              max_episode_steps=3)
+    hp, dp = cls(host_chunk_envs=1 << 20, **kw), cls(**kw)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(4):
+        a = torch.randint(0, 4, (16, n), dtype=torch.int8, device="cuda", generator=gen)
+        if layout == "packed":
+            a = dp.pack(a)
+        obs, rew, term, trunc, info = hp.step(a.cpu().numpy())
+        dp.step_device(a)
+        if layout == "packed":
+            assert (torch.from_numpy(obs.view(np.int32)) == dp.packed_state.cpu()).all()
+            assert (torch.from_numpy(info["flags"]) == dp._flags[:n].cpu()).all()
+        else:
+            assert (torch.from_numpy(np.stack(obs)) == dp.state.cpu()).all()
+            assert (torch.from_numpy(info["tabular_state"].view(np.int32)) == dp._index[:n].cpu()).all()
+            assert (torch.from_numpy(info["unsafe"]) == dp._unsafe[:n].cpu().bool()).all()
+            assert (torch.from_numpy(trunc) == dp._truncated[:n].cpu().bool()).all()
+        assert (torch.from_numpy(rew).view(torch.int32) == dp._reward[:n].cpu().view(torch.int32)).all()
+    assert hp.stats() == dp.stats()
