@@ -188,6 +188,8 @@ def time_device_path(batches, steps, warmup, dist, device, sampler_index, reduce
     main = torch.cuda.current_stream(device)
     streams = [main] if len(batches) == 1 else [torch.cuda.Stream(device=device) for _ in batches]
     slots = [[b["env"]._bind(a) for a in b["ring"]] for b in batches]
+    for b, sl in zip(batches, slots):
+        b["env"].prepare_step_many(sl)          # small shards: the graph gc_step_many replays, built before any timing
 
     def run(lo, hi):
         for s in streams:
@@ -606,7 +608,9 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
     batches = build_batches(workload, device, rank)
     n_rank = sum(b["n"] for b in batches)
     reducer = StatsReducer()
-    ms, launches, clocks, host_us = time_device_path(batches, steps, warmup, dist, device, device.index, reducer)
+    # the per-iteration all-reduce of the statistics belongs to the multi-GPU path; one rank has nothing to reduce
+    in_loop = reducer if dist is not None else None
+    ms, launches, clocks, host_us = time_device_path(batches, steps, warmup, dist, device, device.index, in_loop)
     single = dist is None and side
     graph_res = None
     if WORKLOADS[workload]["l2_resident"] and single:
@@ -666,7 +670,7 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
     has_cell = any(kind == "cellular" for kind, _, _ in WORKLOADS[workload]["parts"])
     pbatches = build_batches(workload, device, rank, packed=True)
     if has_cell:
-        p_ms, p_launches, _, p_host_us = time_device_path(pbatches, steps, warmup, dist, device, device.index, reducer)
+        p_ms, p_launches, _, p_host_us = time_device_path(pbatches, steps, warmup, dist, device, device.index, in_loop)
         res["packed"] = {"value": world * n_rank * steps / (p_ms * 1e-3), "ms_per_step": p_ms / steps,
                          "gpu_launches": p_launches * world, "host_us_per_launch": round(p_host_us, 2),
                          "layout": "cellular sub-batches: one 32-bit word per env for the state, one for the action "
@@ -779,7 +783,7 @@ def main():
     # side workloads: the launch-bound configs 2 and 3 on one GPU (with enough steps that a short driver run is
     # not a pipeline-fill measurement), the mixed multi-GPU config 5 at every N
     extra = {}
-    side_steps = max(args.steps, 500)
+    side_steps = max(args.steps, 2000)
     if not args.no_extra:
         for w in (("cfg2", "cfg3", "cfg5") if world == 1 else ("cfg5",)):
             if w != args.workload:

@@ -19,7 +19,7 @@ POLICY_RANDOM, POLICY_TABLE = 0, 1
 
 EXPORTS = ["gc_abi_version", "gc_last_error", "gc_create", "gc_destroy", "gc_set_tables", "gc_set_final_obs",
            "gc_set_global_step", "gc_get_global_step", "gc_sync_global_step", "gc_launch_count", "gc_reset", "gc_step",
-           "gc_bind_step", "gc_step_bound", "gc_step_many", "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode",
+           "gc_bind_step", "gc_step_bound", "gc_step_many", "gc_prepare_step_many", "gc_step_host", "gc_rollout", "gc_poll_status", "gc_encode",
            "gc_decode", "gc_encode_mixed", "gc_decode_mixed", "gc_reset_packed", "gc_step_packed", "gc_bind_step_packed",
            "gc_step_host_packed", "gc_pack_cells", "gc_unpack_cells"]
 FLAG_UNSAFE, FLAG_TRUNCATED, FLAG_COUNT_SHIFT = 1, 2, 2
@@ -83,6 +83,7 @@ def load():
     L.gc_decode.argtypes = [C.c_int, i64, i64, C.c_int32, C.c_int32, vp, vp, vp]
     i32 = C.c_int32
     L.gc_step_many.argtypes = [vp, vp, i32, i32, vp]
+    L.gc_prepare_step_many.argtypes = [vp, vp, i32]
     L.gc_encode_mixed.argtypes = [C.c_int, i64, i64, i32, vp, vp, vp, vp, vp]
     L.gc_decode_mixed.argtypes = [C.c_int, i64, i64, i32, vp, vp, vp, vp, vp]
     L.gc_reset_packed.argtypes = [vp] * 6

@@ -42,6 +42,7 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 constexpr int kHostStreams = 3;
+constexpr int kManyGraphs = 4;
 
 // Entry points run on the handle's device but leave the caller's current device untouched (a torch
 // process may be driving several GPUs).
@@ -87,6 +88,8 @@ struct gc_env {
     uint32_t *d_done;               // block-arrival counter of the step kernels
     uint2 *d_pair_lut;            // fast-path table (GC_PAIR_LUT_ENTRIES), device memory owned by the handle
     uint2 *d_packed_lut;          // the same rules in the packed layout's index order (gc_cell_packed.cu)
+    uint2 *d_pair8_lut;           // 5..8 levels, deterministic (gc_cell_pair8.cu): GC_PAIR8_ENTRIES entries
+    bool pair8_ok;
     int8_t *final_state;          // gc_set_final_obs: optional extra output of every int8-layout step
     bool fast_ok;
     StepIO bound[GC_MAX_BINDINGS];  // gc_bind_step slots
@@ -95,6 +98,9 @@ struct gc_env {
     cudaStream_t hstream[kHostStreams];
     cudaEvent_t hevent[kHostStreams];
     bool host_ready;
+    // gc_step_many: instantiated CUDA graphs of one pass over a slot list (launch-bound batch sizes)
+    struct ManyGraph { int32_t slots[GC_MAX_BINDINGS]; int32_t n_slots; cudaGraphExec_t exec; } many[kManyGraphs];
+    int n_many;
 };
 
 namespace {
@@ -191,6 +197,14 @@ int launch_packed(gc_env *env, const PackedIO &io, cudaStream_t st)
     return GC_OK;
 }
 
+// cached gc_step_many graphs hold the pointer sets of the bindings they were captured from
+void drop_many_graphs(gc_env *env)
+{
+    for (int i = 0; i < env->n_many; ++i)
+        if (env->many[i].exec) cudaGraphExecDestroy(env->many[i].exec);
+    env->n_many = 0;
+}
+
 int host_streams(gc_env *env)
 {
     if (!env->host_ready) {
@@ -228,6 +242,8 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
             e = gc_launch_cell_tma_step(env->tab, io, env->d_pair_lut, env->n_sm, st);
         else if (env->fast_ok)
             e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, mode, env->n_sm, st);
+        else if (env->pair8_ok && mode == GC_RNG_NONE && !io.se_row)
+            e = gc_launch_cell_pair8_step(env->tab, io, env->d_pair8_lut, env->n_sm, st);
         else
             e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);
     } else {
@@ -319,6 +335,7 @@ int gc_destroy(gc_env *env)
 {
     if (!env) return GC_OK;
     DeviceGuard guard_(env->cfg.device);
+    drop_many_graphs(env);
     if (env->host_ready)
         for (int i = 0; i < kHostStreams; ++i) {
             cudaStreamDestroy(env->hstream[i]);
@@ -327,6 +344,7 @@ int gc_destroy(gc_env *env)
     if (env->d_status) cudaFree(env->d_status);
     if (env->d_pair_lut) cudaFree(env->d_pair_lut);
     if (env->d_packed_lut) cudaFree(env->d_packed_lut);
+    if (env->d_pair8_lut) cudaFree(env->d_pair8_lut);
     if (env->grid.lut) cudaFree(const_cast<uint32_t *>(env->grid.lut));
     delete env;
     return GC_OK;
@@ -341,6 +359,7 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     const int C = env->cfg.n_cells, S = env->cfg.n_states, A = env->cfg.n_actions;
     const bool noise = (env->cfg.flags & GC_F_NOISE) != 0;
     if (noise && (!t->noisy || !t->draws)) return fail(GC_ERR_INVALID, "GC_F_NOISE needs the noisy and draws tables");
+    drop_many_graphs(env);                     // captured kernel nodes carry the tables by value
     CellTables &tab = env->tab;
     std::memset(&tab, 0, sizeof(tab));
     for (int s = 0; s < S; ++s)
@@ -423,6 +442,19 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         if (!env->d_packed_lut) GC_CUDA(cudaMalloc(&env->d_packed_lut, sizeof(lut)));
         GC_CUDA(cudaMemcpy(env->d_packed_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     }
+    // ---- 5..8 levels, deterministic: 3-bit pair table (gc_cell_pair8.cu) ---------------------------------
+    env->pair8_ok = !env->fast_ok && S <= 8 && A <= 8 && !ragged && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
+    for (int j = 3; j < C && env->pair8_ok; ++j)
+        if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
+            env->pair8_ok = false;
+    if (env->pair8_ok) {
+        std::unique_ptr<uint2[]> lut8(new (std::nothrow) uint2[GC_PAIR8_ENTRIES]);
+        if (!lut8) return fail(GC_ERR_INVALID, "out of host memory");
+        gc_build_pair8_lut(t, C, S, A, lut8.get(), &tab.unsafe_rows8);
+        GC_ON_DEVICE(env->cfg.device);
+        if (!env->d_pair8_lut) GC_CUDA(cudaMalloc(&env->d_pair8_lut, GC_PAIR8_ENTRIES * sizeof(uint2)));
+        GC_CUDA(cudaMemcpy(env->d_pair8_lut, lut8.get(), GC_PAIR8_ENTRIES * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
     env->tables_set = true;
     return GC_OK;
 }
@@ -431,6 +463,7 @@ int gc_set_final_obs(gc_env *env, int8_t *final_state)
 {
     if (int rc = check_env(env)) return rc;
     env->final_state = final_state;
+    drop_many_graphs(env);
     for (int i = 0; i < GC_MAX_BINDINGS; ++i)
         if (env->bound_set[i] == 1) env->bound[i].final_state = final_state;
     return GC_OK;
@@ -522,6 +555,7 @@ int gc_bind_step(gc_env *env, int32_t slot, const int8_t *actions, int8_t *state
                                unsafe, count, se_row, nullptr, stats);
     env->bound[slot].done_ctr = env->d_done;
     env->bound_set[slot] = 1;
+    drop_many_graphs(env);
     return GC_OK;
 }
 
@@ -546,6 +580,60 @@ int gc_step_bound(gc_env *env, int32_t slot, void *stream)
     return launch_bound(env, slot, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+// The instantiated graph of one pass over `slots` (one kernel node per bound step, chained by the programmatic
+// dependency edges the launches carry), captured on a stream of the handle; NULL if it cannot be built.
+cudaGraphExec_t many_graph(gc_env *env, const int32_t *slots, int32_t n_slots)
+{
+    for (int i = 0; i < env->n_many; ++i)
+        if (env->many[i].n_slots == n_slots && std::memcmp(env->many[i].slots, slots, n_slots * sizeof(int32_t)) == 0)
+            return env->many[i].exec;
+    if (n_slots > GC_MAX_BINDINGS || host_streams(env) != GC_OK) return nullptr;
+    if (env->n_many == kManyGraphs) drop_many_graphs(env);
+    cudaStream_t cap = env->hstream[0];
+    const int64_t launches = env->launches, step = env->global_step;      // capturing executes nothing
+    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    int rc = GC_OK;
+    for (int32_t i = 0; i < n_slots && rc == GC_OK; ++i) rc = launch_bound(env, slots[i], cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    env->launches = launches; env->global_step = step;
+    cudaGraphExec_t exec = nullptr;
+    if (rc == GC_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != GC_OK || e != cudaSuccess || !exec) { cudaGetLastError(); return nullptr; }
+    gc_env::ManyGraph &m = env->many[env->n_many++];
+    std::memcpy(m.slots, slots, n_slots * sizeof(int32_t));
+    m.n_slots = n_slots;
+    m.exec = exec;
+    return exec;
+}
+
+// Graph replay pays off where the HOST call per kernel is the bound: short kernels.  Measured (same box, 2000
+// steps): 65,536 envs 15.0 -> 20.7 G env-steps/s, 2^20 grid-world envs 147.5 -> 149.0 G; with 4M-env kernels
+// (40 us each) the full dependency at every graph boundary costs more than the host calls saved (0.878 -> 0.857
+// of the roofline), so larger shards keep plain launches.
+constexpr int64_t kManyGraphMaxEnvs = 1 << 21;
+
+bool many_graphs_enabled(const gc_env *env)
+{
+    static const bool on = [] { const char *v = std::getenv("GC_B200_STEP_MANY_GRAPH"); return !(v && v[0] == '0'); }();
+    return on && env->cfg.n_envs <= kManyGraphMaxEnvs;
+}
+}  // namespace
+
+int gc_prepare_step_many(gc_env *env, const int32_t *slots, int32_t n_slots)
+{
+    if (!env || !slots || n_slots < 1) return fail(GC_ERR_INVALID, "gc_prepare_step_many: bad arguments");
+    if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
+    for (int32_t i = 0; i < n_slots; ++i)
+        if (slots[i] < 0 || slots[i] >= GC_MAX_BINDINGS || !env->bound_set[slots[i]])
+            return fail(GC_ERR_INVALID, "no binding in slot %d", slots[i]);
+    GC_ON_DEVICE(env->cfg.device);
+    if (many_graphs_enabled(env) && n_slots >= 2) many_graph(env, slots, n_slots);   // best effort: plain launches otherwise
+    return GC_OK;
+}
+
 int gc_step_many(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t n_steps, void *stream)
 {
     GC_NVTX("gc_step_many");
@@ -553,7 +641,22 @@ int gc_step_many(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t n_s
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     GC_ON_DEVICE(env->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int32_t i = 0; i < n_steps; ++i)
+    int32_t done = 0;
+    // Launch-bound batch sizes: whole passes over the slot list are replayed from a cached CUDA graph (one host
+    // call per n_slots kernels instead of one per kernel; the RNG step counter lives in device memory, so every
+    // replay draws fresh numbers).  Not while the caller's stream is itself being captured.
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (many_graphs_enabled(env) && n_slots >= 2 && n_steps >= 2 * n_slots &&
+        cudaStreamIsCapturing(st, &capturing) == cudaSuccess && capturing == cudaStreamCaptureStatusNone) {
+        if (cudaGraphExec_t exec = many_graph(env, slots, n_slots)) {
+            for (; done + n_slots <= n_steps; done += n_slots) {
+                GC_CUDA(cudaGraphLaunch(exec, st));
+                env->launches += n_slots;
+                env->global_step += n_slots;
+            }
+        }
+    }
+    for (int32_t i = done; i < n_steps; ++i)
         if (int rc = launch_bound(env, slots[i % n_slots], st)) return rc;
     return GC_OK;
 }
@@ -772,6 +875,7 @@ int gc_bind_step_packed(gc_env *env, int32_t slot, const uint32_t *actions, uint
                                              final_state, se_row, stats);
     env->bound_packed[slot].done_ctr = env->d_done;
     env->bound_set[slot] = 2;
+    drop_many_graphs(env);
     return GC_OK;
 }
 

@@ -68,18 +68,10 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             const int i = threadIdx.x + k * kGridThreads;
             if (i < LUT_VEC) lut_reg[k] = src[i];
         }
-    } else {
-#ifndef GC_GRID_NO_L1_PREFETCH
-        // The table is read through L1, which starts every launch empty: without help the first lookups of a
-        // block miss to L2 AFTER the state words have arrived (a second L2 round trip on the critical path of a
-        // 7 us launch).  Each block therefore prefetches the whole 40 KB table into its SM's L1 here -- no
-        // register, no dependency -- while the previous step kernel of the stream drains (before pdl_wait) and
-        // the first state words are in flight.
-        constexpr int kSectors = (GC_GRID_LUT_ENTRIES * 4 + 31) / 32;
-        for (int i = threadIdx.x; i < kSectors; i += kGridThreads)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(gp.lut) + static_cast<size_t>(i) * 32));
-#endif
     }
+    // (Round 2 tried a `prefetch.global.L1` sweep over the table here for the LUT_GLOBAL variant, to take the L2
+    // round trip of the first lookups off the critical path: 7.22 against 7.08 us per step at 2^20 envs on the
+    // same box -- the 1,250 prefetches per block cost more than the misses they save; removed.)
     pdl_launch_dependents();
     pdl_wait();
     uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;

@@ -109,6 +109,8 @@ struct CellTables {
     double   noise_prob;             // for the replay path (compares doubles like the reference)
     // packed layout (gc_cell_packed.cu)
     uint32_t init_packed;            // initial state, 2 bits per cell
+    // 5..8 levels (gc_cell_pair8.cu): byte s0' = set of levels x with SE[j >= 2][s0'][x] == unsafe
+    unsigned long long unsafe_rows8;
 };
 
 struct GridParams {
@@ -142,6 +144,12 @@ cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, co
 // TMA bulk-staged variant of the deterministic pair-table step for wide envs (gc_cell_tma.cu)
 cudaError_t gc_launch_cell_tma_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
                                     cudaStream_t stream);
+// 5..8 levels / actions, deterministic (gc_cell_pair8.cu): 4096 pair entries [a_d][s_d][a_c][s_c] (3-bit digits)
+// followed by 64 single-cell entries [a][s]
+#define GC_PAIR8_PAIRS 4096
+#define GC_PAIR8_ENTRIES (GC_PAIR8_PAIRS + 64)
+void gc_build_pair8_lut(const gc_cell_tables *t, int C, int S, int A, uint2 *lut, unsigned long long *unsafe_rows8);
+cudaError_t gc_launch_cell_pair8_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm, cudaStream_t stream);
 // packed layout: lut = GC_PAIR_LUT_ENTRIES entries in the packed index order (gc_build_packed_lut)
 void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut);
 cudaError_t gc_launch_cell_packed_step(const CellTables &tab, const PackedIO &io, const uint2 *lut, bool noise,

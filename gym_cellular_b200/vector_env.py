@@ -477,13 +477,23 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         binding `slots[i % len(slots)]` (slots from `_bind` / `bind_step(...).slot`).  The launches are
         chained by programmatic dependent launch and no Python runs between them -- the per-step loop of
         launch-bound batch sizes without capturing a CUDA graph."""
+        arr = self._slot_array(slots)
+        st = (torch.cuda.current_stream(self.device) if stream is None else stream).cuda_stream
+        _lib.check(self._lib.gc_step_many(self._h, arr, len(arr), int(n_steps), st))
+
+    def _slot_array(self, slots):
         key = tuple(int(x) for x in slots)
         cache = self.__dict__.setdefault("_slot_arrays", {})
         arr = cache.get(key)
         if arr is None:
             arr = cache[key] = (C.c_int32 * len(key))(*key)
-        st = (torch.cuda.current_stream(self.device) if stream is None else stream).cuda_stream
-        _lib.check(self._lib.gc_step_many(self._h, arr, len(key), int(n_steps), st))
+        return arr
+
+    def prepare_step_many(self, slots):
+        """Builds the CUDA graph `step_many` replays for this slot list ahead of time (small shards only; no step
+        is executed), so that the first `step_many` does not pay for the capture."""
+        arr = self._slot_array(slots)
+        _lib.check(self._lib.gc_prepare_step_many(self._h, arr, len(arr)))
 
     def rollout(self, n_steps, policy=None):
         """Fused K-step rollout: `n_steps` steps per env inside one kernel, actions generated on the

@@ -279,6 +279,11 @@ def test_step_many_bound_and_graph(B, O):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora)
     assert env.sync_step_counter() == 27
+    env.step_many(slots, 29)                                           # 3 graph replays of the 8-slot pass + 5 plain launches
+    for i in range(29):
+        ora.step(acts[i % 8])
+    assert_matches_oracle(env, ora)
+    assert env.sync_step_counter() == 56 and env.launch_count >= 56
 
 
 def test_make_vector_env_layouts_and_debug_ids(B):

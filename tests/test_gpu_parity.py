@@ -1096,3 +1096,34 @@ def test_host_path_at_bench_size(B, layout):
             assert (torch.from_numpy(trunc) == dp._truncated[:n].cpu().bool()).all()
         assert (torch.from_numpy(rew).view(torch.int32) == dp._reward[:n].cpu().view(torch.int32)).all()
     assert hp.stats() == dp.stats()
+
+
+@pytest.mark.parametrize("C,S", [(1, 5), (2, 8), (3, 6), (5, 5), (10, 8), (9, 7), (13, 5), (4, 8)])
+def test_pair8_kernel_vs_oracle(B, O, C, S):
+    """5..8 levels, deterministic: the 3-bit pair-table kernel (gc_cell_pair8.cu) against the oracle, with the
+    fused auto-reset, the final observation and ragged batch sizes; and against the generic per-cell kernel."""
+    n = 5003
+    difficulty = "hard" if C % 2 else "easy"
+    reward = "multiple_optima" if S % 2 else "right_polarizing"
+    kw = dict(num_envs=n, n_cells=C, n_states=S, difficulty=difficulty, reward_func=getattr(B.tables, reward),
+              max_episode_steps=5, emit_side_effects=False)
+    env = B.CellularVectorEnv(emit_final_obs=True, **kw)
+    gen = B.CellularVectorEnv(force_generic_kernel=True, **kw)
+    ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, difficulty=difficulty, reward=reward, max_episode_steps=5)
+    free = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, difficulty=difficulty, reward=reward)
+    rng = np.random.default_rng(C * 10 + S)
+    for t in range(12):
+        a = rng.integers(0, S, size=(C, n)).astype(np.int8)
+        free.state[:], free.t[:] = ora.state, ora.t
+        env.step_device(dev(a))
+        gen.step_device(dev(a))
+        ora.step(a)
+        free.step(a)
+        assert_matches_oracle(env, ora, check_se=False)
+        assert (host(env._final[:, :n]) == free.state).all()
+        # (pair sums are rounded once per pair, the generic kernel adds cell by cell: rewards agree to rounding)
+        np.testing.assert_allclose(host(env._reward[:n]), host(gen._reward[:n]), rtol=REWARD_RTOL, atol=REWARD_ATOL)
+        assert torch.equal(env.state, gen.state) and torch.equal(env._unsafe[:n], gen._unsafe[:n])
+        assert torch.equal(env._count[:n], gen._count[:n]) and torch.equal(env._index[:n], gen._index[:n])
+    s = env.stats()
+    assert s["env_steps"] == 12 * n == ora.stats[0] and s["unsafe_steps"] == ora.stats[1] and s["count_sum"] == ora.stats[2]
