@@ -264,6 +264,7 @@ const char *gc_last_error(void) { return g_err; }
 
 int gc_create(const gc_config *cfg, gc_env **out)
 {
+    GC_NVTX("gc_create");
     if (!cfg || !out) return fail(GC_ERR_INVALID, "cfg/out is NULL");
     if (cfg->struct_size != sizeof(gc_config))
         return fail(GC_ERR_INVALID, "gc_config.struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(gc_config));
@@ -352,6 +353,7 @@ int gc_destroy(gc_env *env)
 
 int gc_set_tables(gc_env *env, const gc_cell_tables *t)
 {
+    GC_NVTX("gc_set_tables");
     if (int rc = check_env(env)) return rc;
     if (env->cfg.kind != GC_KIND_CELLULAR) return fail(GC_ERR_INVALID, "tables apply to the cellular family only");
     if (!t || !t->move || !t->reward || !t->side_effects || !t->counted || !t->initial_state)
@@ -498,6 +500,7 @@ int64_t gc_launch_count(const gc_env *env) { return env ? env->launches : -1; }
 
 int gc_reset(gc_env *env, const uint8_t *mask, int8_t *state, int32_t *t, uint32_t *index, void *stream)
 {
+    GC_NVTX("gc_reset");
     if (int rc = check_env(env)) return rc;
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     if (!state || !t) return fail(GC_ERR_INVALID, "state/t is NULL");
@@ -524,6 +527,7 @@ int gc_step(gc_env *env, int64_t env_begin, int64_t env_count, const int8_t *act
             uint8_t *unsafe, uint8_t *count, int8_t *se_row, const double *replay_u, int64_t *stats,
             void *stream)
 {
+    GC_NVTX("gc_step");
     if (int rc = check_env(env)) return rc;
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     if (!actions || !state || !t || !reward || !index || !terminated || !truncated || !unsafe || !count)
@@ -668,6 +672,7 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
                  uint8_t *d_unsafe, uint8_t *d_count, int8_t *d_se_row, int64_t *d_stats,
                  int64_t chunk_envs)
 {
+    GC_NVTX("gc_step_host");
     if (int rc = check_env(env)) return rc;
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     if (!h_actions || !d_actions || !d_state || !d_t || !d_reward || !d_index || !d_terminated ||
@@ -708,6 +713,7 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
 int gc_rollout(gc_env *env, int32_t n_steps, int32_t policy_kind, const int32_t *policy, int8_t *state,
                int32_t *t, uint32_t *index, float *ret, int32_t *n_unsafe, int64_t *stats, void *stream)
 {
+    GC_NVTX("gc_rollout");
     if (int rc = check_env(env)) return rc;
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     if (!state || !t || !index || !ret || !n_unsafe) return fail(GC_ERR_INVALID, "a required device pointer is NULL");
@@ -745,6 +751,7 @@ int gc_rollout(gc_env *env, int32_t n_steps, int32_t policy_kind, const int32_t 
 
 int gc_poll_status(gc_env *env, void *stream)
 {
+    GC_NVTX("gc_poll_status");
     if (int rc = check_env(env)) return rc;
     GC_ON_DEVICE(env->cfg.device);
     unsigned long long word = 0;
@@ -804,6 +811,7 @@ int check_mixed(const char *who, int64_t n, int64_t ld, int32_t n_cells, const i
 int gc_encode_mixed(int device, int64_t n, int64_t ld, int32_t n_cells, const int32_t *radix, const int32_t *min,
                     const int8_t *cells, uint32_t *index, void *stream)
 {
+    GC_NVTX("gc_encode_mixed");
     if (!cells || !index) return fail(GC_ERR_INVALID, "gc_encode_mixed: cells/index is NULL");
     if (int rc = check_mixed("gc_encode_mixed", n, ld, n_cells, radix, min)) return rc;
     GC_ON_DEVICE(device);
@@ -815,6 +823,7 @@ int gc_encode_mixed(int device, int64_t n, int64_t ld, int32_t n_cells, const in
 int gc_decode_mixed(int device, int64_t n, int64_t ld, int32_t n_cells, const int32_t *radix, const int32_t *min,
                     const uint32_t *index, int8_t *cells, void *stream)
 {
+    GC_NVTX("gc_decode_mixed");
     if (!cells || !index) return fail(GC_ERR_INVALID, "gc_decode_mixed: cells/index is NULL");
     if (int rc = check_mixed("gc_decode_mixed", n, ld, n_cells, radix, min)) return rc;
     GC_ON_DEVICE(device);
@@ -844,6 +853,7 @@ int gc_step_packed(gc_env *env, int64_t env_begin, int64_t env_count, const uint
                    int32_t *t, float *reward, uint32_t *index, uint8_t *flags, uint32_t *final_state,
                    uint32_t *se_row, int64_t *stats, void *stream)
 {
+    GC_NVTX("gc_step_packed");
     if (int rc = check_env(env)) return rc;
     if (!env->tables_set) return fail(GC_ERR_STATE, "gc_set_tables has not been called");
     if (int rc = check_packed(env)) return rc;

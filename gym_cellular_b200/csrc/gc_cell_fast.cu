@@ -42,6 +42,21 @@ constexpr int pair_min_blocks(int c, int rng)
     return c < 4 ? GC_PAIR_MINB_NARROW : GC_PAIR_MINB;
 }
 
+// Table replication (A/B switch, round 2): with GC_PAIR_REP_LOG2 = 4 the deterministic kernels of wide envs keep
+// 16 copies of the 256-entry pair table (entry i of replica r at word 16 i + r, lane l reads replica l % 16), so
+// that the 16 lanes of a half-warp never meet on a bank pair: profiles/r01_kernel_cfg4.md counted 70 % of the
+// shared-memory wavefronts of config 4 as conflicts.  See profiles/r02_tuning_log.md for the measurement.
+#ifndef GC_PAIR_REP_LOG2
+#define GC_PAIR_REP_LOG2 0
+#endif
+#ifndef GC_PAIR_REP_MIN_C
+#define GC_PAIR_REP_MIN_C 12
+#endif
+__host__ __device__ constexpr int pair_rep_log2(int c, int rng)
+{
+    return (rng == GC_RNG_NONE && c >= GC_PAIR_REP_MIN_C) ? GC_PAIR_REP_LOG2 : 0;
+}
+
 // Everything a thread carries across the cell groups of its four envs.  The low halves of the info
 // words (count byte, presence / flag byte) are accumulated two envs per register (16-bit lanes: envs
 // 0, 1 and envs 2, 3): up to 8 pairs of count <= 2 and of presence / flag bytes <= 0x1F never carry
@@ -103,7 +118,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
             for (int e = 0; e < kEPT; ++e) {
                 uint32_t ix = byte_of(pidx, e);
                 if (RNG != GC_RNG_NONE) ix |= ((fb[e] >> i) & 3u) << 8;
-                const uint2 ent = s_pair[ix];
+                const uint2 ent = s_pair[ix << pair_rep_log2(C, RNG)];     // s_pair points at this lane's replica
                 if (FIRST && i == 0) acc.r[e] = __uint_as_float(ent.y); else acc.r[e] += __uint_as_float(ent.y);
                 inf[e] = ent.x;
             }
@@ -173,7 +188,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     constexpr int NG = C / 4, R = C % 4;                        // full groups, cells in the tail group
     constexpr int N_PAIR = (RNG == GC_RNG_NONE) ? 256 : GC_PAIR_LUT_PAIRS;
     constexpr int N_SINGLE = (RNG == GC_RNG_NONE) ? 16 : 32;
-    __shared__ uint2 s_pair[N_PAIR];
+    constexpr int REP_LOG2 = pair_rep_log2(C, RNG), REP = 1 << REP_LOG2;
+    __shared__ uint2 s_pair_all[N_PAIR * REP];
+    const uint2 *const s_pair = s_pair_all + (threadIdx.x & (REP - 1));
     __shared__ uint2 s_single[N_SINGLE];
     __shared__ uint8_t s_se[WITH_SE ? C : 1][GC_TBL];
     __shared__ unsigned long long s_stats[5];
@@ -207,7 +224,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     }
     step_counter_read(io, &s_ctr);
 #pragma unroll
-    for (int k = 0; k < LUT_PER_THREAD; ++k) s_pair[threadIdx.x + k * kThreads] = lut_pair[k];
+    for (int k = 0; k < LUT_PER_THREAD; ++k)
+#pragma unroll
+        for (int r = 0; r < REP; ++r) s_pair_all[((threadIdx.x + k * kThreads) << REP_LOG2) + r] = lut_pair[k];
     if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut_single;
     if (WITH_SE)
         for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];

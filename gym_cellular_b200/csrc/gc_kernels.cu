@@ -27,7 +27,7 @@ namespace {
 // cell c is computed; per (env, cell) one 64-bit shared load for the (level, action) entry, one for the
 // side-effect code.  ~50 registers, so eight blocks of 256 threads stay resident per SM.
 template <int RNG>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, RNG == GC_RNG_PHILOX ? 3 : 4)      // Philox variant: 85 registers, no spills
 cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ StepIO io)
 {
     __shared__ uint2 s_sa[GC_TBL];                 // .x packed move/noisy/draws, .y reward bits

@@ -5,7 +5,8 @@ cells3states3actions3.py:116-125), so a global batch is cut into contiguous glob
 rank steps its own `CellularVectorEnv` with `env_id_offset` = first global id.  Philox streams are
 keyed by GLOBAL env id, hence results are independent of the world size.  The only exchange is one
 all-reduce(SUM) of the int64 episode-statistics vector per rollout iteration (NCCL over
-NVLink/NVSwitch on GPUs; any torch.distributed backend works -- the CPU tests use gloo).
+NVLink/NVSwitch on GPUs, ordered in the stepping stream; any torch.distributed backend works -- the CPU
+tests use gloo).
 """
 import torch
 
@@ -38,11 +39,19 @@ def make_sharded_env(n_global, rank=None, world_size=None, **kwargs):
 
 
 class StatsReducer:
-    """All-reduce of the episode statistics, issued once per iteration on a side stream so that it
-    overlaps the next steps (the vector is 64 bytes: pure latency)."""
+    """All-reduce of the episode statistics, once per iteration (the vector is 64 bytes: pure latency).
 
-    def __init__(self, group=None):
+    The reduction is ordered IN the stepping stream (`in_stream=True`, the default): the step kernels are
+    persistent one-wave grids that hold every resident-block slot of the GPU, so an NCCL kernel running beside
+    them on a side stream takes a slot away -- one block of the step kernel then runs as a second wave and the
+    step takes twice as long for as long as the NCCL kernel spins on its peers (measured on 2 GPUs: 235 instead
+    of 191 us per config-4 step with a side-stream reduction every 64 steps).  In the stream it costs one
+    ~20-30 us kernel per iteration and nothing else.  `in_stream=False` keeps the side-stream variant for
+    callers whose kernels leave room."""
+
+    def __init__(self, group=None, in_stream=True):
         self.group = group
+        self.in_stream = in_stream
         self._stream = None
         self._buf = None
         self._work = None
@@ -54,7 +63,7 @@ class StatsReducer:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             self._work = None
             return self
-        if self._buf.is_cuda:
+        if self._buf.is_cuda and not self.in_stream:
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=self._buf.device)
             self._stream.wait_stream(torch.cuda.current_stream(self._buf.device))
@@ -62,23 +71,22 @@ class StatsReducer:
                 self._work = dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:
             self._work = dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if self._buf.is_cuda:
+                self._work.wait()          # orders the current stream after the collective; does not block the host
         return self
 
     def wait(self):
         """Orders the current stream after the pending reduction (no host synchronisation)."""
         if self._work is not None:
             self._work.wait()
-            if self._buf.is_cuda:
+            if self._buf.is_cuda and self._stream is not None and not self.in_stream:
                 torch.cuda.current_stream(self._buf.device).wait_stream(self._stream)
             self._work = None
         return self
 
     def result(self):
         """Global totals as a dict (waits for the reduction)."""
-        if self._work is not None:
-            self._work.wait()
-            if self._buf.is_cuda:
-                torch.cuda.current_stream(self._buf.device).wait_stream(self._stream)
+        self.wait()
         s = self._buf.cpu().tolist()
         return {"env_steps": s[0], "unsafe_steps": s[1], "count_sum": s[2], "episodes_truncated": s[3],
                 "reward_sum": s[4] / 2.0 ** 24}
