@@ -107,6 +107,9 @@ class ClockSampler:
                         self.reasons.add(name)
 
     def _run(self):
+        # first sample 1 ms into the region: by then the launches of a short region are queued (an NVML query
+        # takes a driver lock that concurrent kernel launches also need), and the kernels are running
+        self._stop.wait(0.001)
         while not self._stop.is_set():
             try:
                 self._poll_once()

@@ -667,6 +667,10 @@ class CellularVectorEnv(gym.vector.VectorEnv):
                  "tabular_state": h["index"][:n].view(np.uint32)}
         if "se_row" in h:
             infos["side_effects"] = h["se_row"][:, :n]
+        if self._final is not None:        # the final observations stay on the device: one extra copy when asked for
+            fin = self._final[:, :n].cpu().numpy()
+            infos["final_obs"] = tuple(fin[c] for c in range(self.n_cells))
+            infos["_final_obs"] = h["truncated"][:n].view(np.bool_)
         return obs, h["reward"][:n], h["terminated"][:n].view(np.bool_), h["truncated"][:n].view(np.bool_), infos
 
 
