@@ -157,7 +157,9 @@ def build_batches(workload, device, rank, n_override=None, packed=False):
         use_packed = packed and kind == "cellular"
         cls = PackedCellularVectorEnv if use_packed else CellularVectorEnv
         env = cls(kind=kind, num_envs=n, device=device, env_seed=0, env_id_offset=offset,
-                  emit_side_effects=False, collect_stats=True, host_chunk_envs=HOST_CHUNK_ENVS, **kw)
+                  emit_side_effects=False, collect_stats=True,
+                  # host-path chunk: 1 M envs on the int8 wire, 2 M on the packed wire (sweeps in profiles/r0*_tuning_log.md)
+                  host_chunk_envs=HOST_CHUNK_ENVS * (2 if use_packed else 1), **kw)
         offset += n
         ring = []
         for _ in range(RING):
@@ -603,14 +605,22 @@ def roofline_of(workload, batches, step_s, tag=None):
     peak, peak_src = measured_peak()
     traffic = ncu_traffic(tag or workload)
     static = WORKLOADS[workload]["l2_resident"]
-    # part of a working set that fits the 126 MB L2 never reaches DRAM: say so from the measured traffic
+    # A working set below the 126 MB L2 stays there from step to step (ncu's DRAM bytes for such a launch are the
+    # cold-cache reads of its replay mode, not steady-state traffic); above it, the measured traffic says how much
+    # of the algorithmic bytes actually reaches DRAM
     dram_share = None if not isinstance(traffic, (int, float)) else traffic / alg_bytes
+    if alg_bytes < 100e6:
+        resident = True
+    elif dram_share is None:
+        resident = static
+    else:
+        resident = "partly" if dram_share < 0.75 else False
     return {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": peak, "unit": "GB/s",
             "frac": alg_bytes / step_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes // len(batches), "bytes_per_env_step": alg_bytes / n_rank,
             "kernels_per_step": len(batches),
             "dram_bytes_over_algorithmic": None if dram_share is None else round(dram_share, 3),
-            "l2_resident": static if dram_share is None else ("partly" if 0.25 <= dram_share < 0.75 else dram_share < 0.25)}
+            "l2_resident": resident}
 
 
 def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps, side=True):
