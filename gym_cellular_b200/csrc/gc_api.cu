@@ -272,6 +272,10 @@ int gc_create(const gc_config *cfg, gc_env **out)
     if (cfg->ld < cfg->n_envs || cfg->ld % 16 != 0)
         return fail(GC_ERR_INVALID, "ld must be a multiple of 16 and >= n_envs");
     if (cfg->max_episode_steps < 0) return fail(GC_ERR_INVALID, "max_episode_steps must be >= 0");
+    // the kernels index their arrays with 32-bit element offsets (one IMAD.WIDE per address)
+    if (cfg->n_cells >= 1 && cfg->ld > (int64_t(1) << 31) / cfg->n_cells)
+        return fail(GC_ERR_INVALID, "n_cells * ld must not exceed 2^31 (%d cells: at most %lld envs per handle)", cfg->n_cells,
+                    (long long)((int64_t(1) << 31) / cfg->n_cells));
     if (cfg->env_id_offset < 0 || cfg->env_id_offset % 4 != 0)
         return fail(GC_ERR_INVALID, "env_id_offset must be a non-negative multiple of 4");
     if (cfg->kind == GC_KIND_CELLULAR) {

@@ -75,7 +75,7 @@ struct EnvAcc {
 template <int N, int C, int RNG, bool WITH_SE, bool FIRST>
 __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io, const uint2 *s_pair,
                                          const uint2 *s_single, const uint8_t (*s_se)[GC_TBL], int c0,
-                                         int64_t e0, int rem, uint32_t gid_lo, uint32_t gid_hi, uint32_t step_counter,
+                                         uint32_t e0, int rem, uint32_t gid_lo, uint32_t gid_hi, uint32_t step_counter,
                                          const int (&tin)[kEPT], uint32_t keep, const uint32_t (&sw)[4],
                                          const uint32_t (&aw)[4], const uint32_t (&fire16)[kEPT], EnvAcc &acc)
 {
@@ -102,9 +102,10 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
             if (e < rem)
 #pragma unroll
                 for (int i = 0; i < N; ++i)
-                    fb[e] |= (io.replay[(e0 + e) * C + c0 + i] < tab.noise_prob ? 1u : 0u) << i;
+                    fb[e] |= (io.replay[static_cast<size_t>(e0 + e) * C + c0 + i] < tab.noise_prob ? 1u : 0u) << i;
     }
-    const int64_t ld = io.ld;
+    // 32-bit element indexes (n_cells * ld <= 2^31, gc_create): an address is one IMAD.WIDE.U32 on the FMA pipe
+    const uint32_t ld = static_cast<uint32_t>(io.ld);
     uint32_t q = 0;                       // index digits of the group folded into one byte per env
     uint32_t rows[4];
 #pragma unroll
@@ -155,11 +156,11 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
                 const uint32_t partner = (FIRST && i == 0) ? byte_of(acc.s1w, e) : byte_of(rows[i], e);
                 sew |= static_cast<uint32_t>(s_se[c0 + i][(s0n * GC_LVL_PAD + partner) & (GC_TBL - 1)]) << (8 * e);
             }
-            st_stream_u32(io.se_row + (c0 + i) * ld + e0, sew);
+            st_stream_u32(io.se_row + ((c0 + i) * ld + e0), sew);
         }
         const uint32_t out = (rows[i] & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c0 + i])) & ~keep);
-        st_stream_u32(io.state + (c0 + i) * ld + e0, out);
-        if (io.final_state) st_stream_u32(io.final_state + (c0 + i) * ld + e0, rows[i]);
+        st_stream_u32(io.state + ((c0 + i) * ld + e0), out);
+        if (io.final_state) st_stream_u32(io.final_state + ((c0 + i) * ld + e0), rows[i]);
         q += out * tab.place4[i];
     }
     const uint32_t place = tab.place[c0];
@@ -168,12 +169,13 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
 }
 
 template <int N>
-__device__ __forceinline__ void load_cells(const StepIO &io, int c0, int64_t e0, uint32_t (&sw)[4], uint32_t (&aw)[4])
+__device__ __forceinline__ void load_cells(const StepIO &io, int c0, uint32_t e0, uint32_t (&sw)[4], uint32_t (&aw)[4])
 {
+    const uint32_t ld = static_cast<uint32_t>(io.ld);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        sw[i] = ld_stream_u32(io.state + (c0 + i) * io.ld + e0);
-        aw[i] = ld_stream_u32(io.actions + (c0 + i) * io.ld + e0);
+        sw[i] = ld_stream_u32(io.state + ((c0 + i) * ld + e0));
+        aw[i] = ld_stream_u32(io.actions + ((c0 + i) * ld + e0));
     }
 }
 
@@ -197,7 +199,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
 
     __shared__ StepCounterShared s_ctr;
 
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
+    const uint32_t stride = gridDim.x * kThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
     // Narrow envs (C < 4: a thread reads only ~10 words per 4 envs) prefetch the inputs of their next
     // 4-env word before computing the current one, to keep enough bytes in flight per SM; the first
     // word's inputs are requested before the tables are staged, so that the two latencies overlap.
@@ -206,7 +208,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
 #endif
     constexpr bool PREFETCH = NG == 0 || GC_PAIR_PREFETCH_WIDE;
     constexpr int G0 = NG > 0 ? 4 : R;                       // cells in the first group
-    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+    uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kThreads + threadIdx.x) * kEPT;
     // the immutable tables are requested first (they may be read while the previous step kernel of the
     // stream is still running), then the data the previous kernel wrote, then the tables are stored
     constexpr int LUT_PER_THREAD = N_PAIR / kThreads;
@@ -218,7 +220,7 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     pdl_wait();
     uint32_t ps[4], pa[4];
     int4 pt = make_int4(0, 0, 0, 0);
-    if constexpr (PREFETCH) if (e0 < io.end) {
+    if constexpr (PREFETCH) if (e0 < e_end) {
         load_cells<G0>(io, 0, e0, ps, pa);
         pt = ld_stream_v4(io.t + e0);
     }
@@ -238,9 +240,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;   // < 2^32 per thread and launch
     long long st_reward = 0;
 #pragma unroll 1
-    for (; e0 < io.end; e0 += stride) {
-        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);    // envs of this word in range
-        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);           // multiple of 4: | e never carries
+    for (; e0 < e_end; e0 += stride) {
+        const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);    // envs of this word in range
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;           // multiple of 4: | e never carries
         const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
 
         uint32_t sa[4], aa[4], sb[4], ab[4];
@@ -250,9 +252,9 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
             for (int i = 0; i < 4; ++i) { sa[i] = ps[i]; aa[i] = pa[i]; }
             t4 = pt;
             if (NG > 1) load_cells<4>(io, 4, e0, sb, ab); else if (NG == 1 && R > 0) load_cells<R>(io, 4, e0, sb, ab);
-            if (e0 + stride < io.end) {
+            if (e0 + stride < e_end) {
                 load_cells<G0>(io, 0, e0 + stride, ps, pa);
-                pt = ld_stream_v4(io.t + e0 + stride);
+                pt = ld_stream_v4(io.t + (e0 + stride));
             }
         } else {
             load_cells<4>(io, 0, e0, sa, aa);

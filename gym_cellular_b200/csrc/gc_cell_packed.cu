@@ -87,8 +87,9 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
     __shared__ StepCounterShared s_ctr;
     const uint32_t REP = 1u << REP_LOG2;
 
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kPackThreads * kEPT;
-    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kPackThreads + threadIdx.x) * kEPT;
+    // 32-bit element indexes (n_cells * ld <= 2^31, gc_create): an address is one IMAD.WIDE.U32 on the FMA pipe
+    const uint32_t stride = gridDim.x * kPackThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
+    uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kPackThreads + threadIdx.x) * kEPT;
     // immutable tables first (they may be read while the previous step kernel of the stream still runs)
     for (int i = threadIdx.x; i < (N_PAIR << REP_LOG2); i += kPackThreads) s_pair[i] = lut[i >> REP_LOG2];
     for (int i = threadIdx.x; i < (N_SINGLE << REP_LOG2); i += kPackThreads) s_single[i] = lut[GC_PAIR_LUT_PAIRS + (i >> REP_LOG2)];
@@ -98,7 +99,7 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
     pdl_launch_dependents();
     pdl_wait();
     int4 ps = make_int4(0, 0, 0, 0), pa = ps, pt = ps;
-    if (e0 < io.end) {
+    if (e0 < e_end) {
         ps = ld_stream_v4(io.state + e0);
         pa = ld_stream_v4(io.actions + e0);
         pt = ld_stream_v4(io.t + e0);
@@ -115,17 +116,17 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
 
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
     long long st_reward = 0;
-    for (; e0 < io.end; e0 += stride) {
-        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
-        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
+    for (; e0 < e_end; e0 += stride) {
+        const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
         const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
         const uint32_t sw4[kEPT] = {(uint32_t)ps.x, (uint32_t)ps.y, (uint32_t)ps.z, (uint32_t)ps.w};
         const uint32_t aw4[kEPT] = {(uint32_t)pa.x, (uint32_t)pa.y, (uint32_t)pa.z, (uint32_t)pa.w};
         const int tin[kEPT] = {pt.x, pt.y, pt.z, pt.w};
-        if (e0 + stride < io.end) {                    // the next word's inputs, before this one is computed
-            ps = ld_stream_v4(io.state + e0 + stride);
-            pa = ld_stream_v4(io.actions + e0 + stride);
-            pt = ld_stream_v4(io.t + e0 + stride);
+        if (e0 + stride < e_end) {                     // the next word's inputs, before this one is computed
+            ps = ld_stream_v4(io.state + (e0 + stride));
+            pa = ld_stream_v4(io.actions + (e0 + stride));
+            pt = ld_stream_v4(io.t + (e0 + stride));
         }
         uint32_t nstate[kEPT], fin[kEPT], idx[kEPT], sew[kEPT];
         uint32_t flags_w = 0;                          // flag bytes of the four envs

@@ -31,9 +31,10 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const int C = tab.n_cells;
-    const int64_t ld = io.ld;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
-    int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
+    // 32-bit element indexes (n_cells * ld <= 2^31, gc_create): an address is one IMAD.WIDE.U32 on the FMA pipe
+    const uint32_t ld = static_cast<uint32_t>(io.ld);
+    const uint32_t stride = gridDim.x * kThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
+    uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kThreads + threadIdx.x) * kEPT;
 
     for (int i = threadIdx.x; i < GC_PAIR8_PAIRS; i += kThreads) s_pair[i] = lut[i];
     if (threadIdx.x < 64) s_single[threadIdx.x] = lut[GC_PAIR8_PAIRS + threadIdx.x];
@@ -47,13 +48,13 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
     long long st_reward = 0;
 #pragma unroll 1
-    for (; e0 < io.end; e0 += stride) {
-        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
+    for (; e0 < e_end; e0 += stride) {
+        const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
         // rows of the first four cells, the episode steps
         uint32_t sw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (i < C) { sw[i] = ld_stream_u32(io.state + i * ld + e0); aw[i] = ld_stream_u32(io.actions + i * ld + e0); }
+            if (i < C) { sw[i] = ld_stream_u32(io.state + (i * ld + e0)); aw[i] = ld_stream_u32(io.actions + (i * ld + e0)); }
         const int4 t4 = ld_stream_v4(io.t + e0);
         int tn[kEPT] = {t4.x + 1, t4.y + 1, t4.z + 1, t4.w + 1};
         uint32_t trunc_w = 0, keep = 0xFFFFFFFFu;
@@ -81,15 +82,15 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
             const uint32_t row_c = prmt(u, v, 0x5410), row_d = prmt(u, v, 0x7632);
             if (first) s0w = row_c;
             const uint32_t out_c = (row_c & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c])) & ~keep);
-            st_stream_u32(io.state + c * ld + e0, out_c);
-            if (io.final_state) st_stream_u32(io.final_state + c * ld + e0, row_c);
+            st_stream_u32(io.state + (c * ld + e0), out_c);
+            if (io.final_state) st_stream_u32(io.final_state + (c * ld + e0), row_c);
             const uint32_t pc = tab.place[c];
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) idx[e] += byte_of(out_c, e) * pc;
             if (pair) {
                 const uint32_t out_d = (row_d & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c + 1])) & ~keep);
-                st_stream_u32(io.state + (c + 1) * ld + e0, out_d);
-                if (io.final_state) st_stream_u32(io.final_state + (c + 1) * ld + e0, row_d);
+                st_stream_u32(io.state + ((c + 1) * ld + e0), out_d);
+                if (io.final_state) st_stream_u32(io.final_state + ((c + 1) * ld + e0), row_d);
                 const uint32_t pd = tab.place[c + 1];
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e) idx[e] += byte_of(out_d, e) * pd;
@@ -122,8 +123,8 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (c + 4 + i < C) {
-                    ns[i] = ld_stream_u32(io.state + (c + 4 + i) * ld + e0);
-                    na[i] = ld_stream_u32(io.actions + (c + 4 + i) * ld + e0);
+                    ns[i] = ld_stream_u32(io.state + ((c + 4 + i) * ld + e0));
+                    na[i] = ld_stream_u32(io.actions + ((c + 4 + i) * ld + e0));
                 }
             do_pair(c, 0);
             if (c + 2 < C) do_pair(c + 2, 2);

@@ -44,18 +44,21 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     extern __shared__ __align__(16) uint32_t s_lut[];          // kGridLutAlloc entries, the first 10,000 staged (unless LUT_GLOBAL)
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
-    const int64_t ld = io.ld;
+    // Element indexes are 32-bit (gc_create bounds n_cells * ld by 2^31): an address is then ONE IMAD.WIDE.U32 on
+    // the FMA pipe instead of an IADD3 / IADD3.X pair on the ALU pipe, which is the pipe that bounds this kernel
+    // (14 addresses per iteration; profiles/r02_kernel_cfg5.md: math_pipe_throttle 2.0).
+    const uint32_t ld = static_cast<uint32_t>(io.ld);
     // Work partition: plain grid-stride loop.  (Round 2 tried contiguous per-block chunks of equal length --
     // a launch of 1.7 waves such as 2^20 envs leaves some SMs with 4 and some with 3 block-iterations under
     // grid-stride -- and measured it SLOWER on the same box: config 3 7.58 against 7.26 us per step, config 5
     // 0.812 against 0.870 of the HBM roofline; 296 separate streams lose the DRAM page locality of one sweep.)
-    const int64_t w_lo = static_cast<int64_t>(blockIdx.x) * kGridThreads, e_end = io.end;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kGridThreads * kEPT;
+    const uint32_t w_lo = blockIdx.x * kGridThreads, e_end = static_cast<uint32_t>(io.end);
+    const uint32_t stride = gridDim.x * kGridThreads * kEPT;
     // The inputs of the NEXT 4-env word are requested before the current one is computed: a thread only
     // reads 32 bytes per word, so without the prefetch too few bytes are in flight per SM to cover the
     // HBM latency (ncu: long-scoreboard stalls dominate at 40 % occupancy).  The first word's inputs are
     // requested before the table is staged, so that the two latencies overlap.
-    int64_t e0 = io.begin + (w_lo + threadIdx.x) * kEPT;
+    uint32_t e0 = static_cast<uint32_t>(io.begin) + (w_lo + threadIdx.x) * kEPT;
     // the immutable table is requested first (possibly while the previous step kernel of the stream is
     // still running: gc_device.cuh, programmatic dependent launch), then the first word's inputs, then
     // the table is stored to shared memory, so that the two latencies overlap
@@ -77,8 +80,8 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     uint32_t p_s0 = 0, p_s1 = 0, p_a0 = 0, p_a1 = 0;
     int4 p_t = make_int4(0, 0, 0, 0);
     if (e0 < e_end) {
-        p_s0 = ld_stream_u32(io.state + e0); p_s1 = ld_stream_u32(io.state + ld + e0);
-        p_a0 = ld_stream_u32(io.actions + e0); p_a1 = ld_stream_u32(io.actions + ld + e0);
+        p_s0 = ld_stream_u32(io.state + e0); p_s1 = ld_stream_u32(io.state + (ld + e0));
+        p_a0 = ld_stream_u32(io.actions + e0); p_a1 = ld_stream_u32(io.actions + (ld + e0));
         p_t = ld_stream_v4(io.t + e0);
     }
     step_counter_read(io, &s_ctr);
@@ -97,14 +100,14 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     for (; e0 < e_end; e0 += stride) {
         const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
-        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
         const uint32_t s0w = p_s0, s1w = p_s1;
         uint32_t a0w = p_a0, a1w = p_a1;
         const int4 t4 = p_t;
         if (e0 + stride < e_end) {
-            const int64_t en = e0 + stride;
-            p_s0 = ld_stream_u32(io.state + en); p_s1 = ld_stream_u32(io.state + ld + en);
-            p_a0 = ld_stream_u32(io.actions + en); p_a1 = ld_stream_u32(io.actions + ld + en);
+            const uint32_t en = e0 + stride;
+            p_s0 = ld_stream_u32(io.state + en); p_s1 = ld_stream_u32(io.state + (ld + en));
+            p_a0 = ld_stream_u32(io.actions + en); p_a1 = ld_stream_u32(io.actions + (ld + en));
             p_t = ld_stream_v4(io.t + en);
         }
         const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
@@ -174,7 +177,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             for (int e = 0; e < kEPT; ++e) {
                 const uint32_t nb = (ent[e] >> 18) & 3u;
                 const bool valid = e < rem;
-                const double *u = io.replay + (valid ? (e0 + e) * 6 : 0);
+                const double *u = io.replay + (valid ? static_cast<size_t>(e0 + e) * 6 : 0);
                 if (nb < 2u && valid && u[0] < gp.dispersal_prob) {
                     const uint32_t b00 = static_cast<uint32_t>(u[1] * 2.0), b10 = static_cast<uint32_t>(u[3] * 2.0);
                     const uint32_t k = static_cast<uint32_t>(u[5] * 2.0);
@@ -204,19 +207,24 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         int tout[kEPT] = {tin[0] + 1, tin[1] + 1, tin[2] + 1, tin[3] + 1};
         if (io.final_state) {                                                // final observation: before the auto-reset
             st_stream_u32(io.final_state + e0, row0);
-            st_stream_u32(io.final_state + ld + e0, row1);
+            st_stream_u32(io.final_state + (ld + e0), row1);
         }
         if (io.max_episode_steps > 0) {
-            uint32_t keep = 0xFFFFFFFFu;
 #pragma unroll
-            for (int e = 0; e < kEPT; ++e)
-                if (tout[e] >= io.max_episode_steps) { tout[e] = 0; trunc_w |= 1u << (8 * e); keep &= ~(0xFFu << (8 * e)); }
-            row0 = (row0 & keep) | (0x0F0F0F0Fu & ~keep);                       // reset codes 15 / 18: grid_world.py:238-259
-            row1 = (row1 & keep) | (0x12121212u & ~keep);
+            for (int e = 0; e < kEPT; ++e) {
+                const bool tr = tout[e] >= io.max_episode_steps;
+                tout[e] = tr ? 0 : tout[e];
+                trunc_w |= (tr ? 1u : 0u) << (8 * e);
+            }
+            const uint32_t gone = trunc_w * 0xFFu;                               // byte mask of the envs that reset
+            row0 = (row0 & ~gone) | (0x0F0F0F0Fu & gone);                       // reset codes 15 / 18: grid_world.py:238-259
+            row1 = (row1 & ~gone) | (0x12121212u & gone);
         }
         float rout[kEPT];
 #pragma unroll
-        for (int e = 0; e < kEPT; ++e) rout[e] = static_cast<float>(byte_of(rew_w, e));
+        // reward byte -> float without a conversion: the byte becomes the low mantissa byte of 2^23 (one PRMT),
+        // minus 2^23 (one FADD on the FMA pipe, which has room; the ALU pipe is what bounds this kernel)
+        for (int e = 0; e < kEPT; ++e) rout[e] = __uint_as_float(prmt(rew_w, 0x4B000000u, 0x7540u + e)) - 8388608.0f;
         const uint32_t x02 = (row0 & 0x00FF00FFu) + 20u * (row1 & 0x00FF00FFu);             // code_0 + 20 code_1
         const uint32_t x13 = ((row0 >> 8) & 0x00FF00FFu) + 20u * ((row1 >> 8) & 0x00FF00FFu);
         const uint32_t iout[kEPT] = {x02 & 0xFFFFu, x13 & 0xFFFFu, x02 >> 16, x13 >> 16};
@@ -228,10 +236,10 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
             st_reward = add_bytes(rew_w & vb, st_reward);
         }
         st_stream_u32(io.state + e0, row0);
-        st_stream_u32(io.state + ld + e0, row1);
+        st_stream_u32(io.state + (ld + e0), row1);
         if (io.se_row) {
             st_stream_u32(io.se_row + e0, se0w);
-            st_stream_u32(io.se_row + ld + e0, se1w);
+            st_stream_u32(io.se_row + (ld + e0), se1w);
         }
         st_stream_v4(io.t + e0, make_int4(tout[0], tout[1], tout[2], tout[3]));
         st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),

@@ -46,12 +46,13 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
     const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? launch_step_counter(io) : 0u;
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
     long long st_reward = 0;
-    const int64_t ld = io.ld;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kEPT;
-    for (int64_t e0 = io.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * kEPT;
-         e0 < io.end; e0 += stride) {
-        const int rem = static_cast<int>(io.end - e0 < kEPT ? io.end - e0 : kEPT);
-        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset + e0);
+    // 32-bit element indexes (n_cells * ld <= 2^31, gc_create): an address is one IMAD.WIDE.U32 on the FMA pipe
+    const uint32_t ld = static_cast<uint32_t>(io.ld);
+    const uint32_t stride = gridDim.x * kThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
+    for (uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kThreads + threadIdx.x) * kEPT;
+         e0 < e_end; e0 += stride) {
+        const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
         const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
         uint32_t sw = ld_stream_u32(io.state + e0), aw = ld_stream_u32(io.actions + e0);
         const int4 t4 = ld_stream_v4(io.t + e0);
@@ -80,8 +81,8 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
         for (int c = 0; c < C; ++c) {
             uint32_t sn = 0, an = 0;
             if (c + 1 < C) {                                  // prefetch the next cell's rows
-                sn = ld_stream_u32(io.state + (c + 1) * ld + e0);
-                an = ld_stream_u32(io.actions + (c + 1) * ld + e0);
+                sn = ld_stream_u32(io.state + ((c + 1) * ld + e0));
+                an = ld_stream_u32(io.actions + ((c + 1) * ld + e0));
             }
             if (RNG == GC_RNG_PHILOX && !wide && (c & 3) == 0) {
 #pragma unroll
@@ -100,7 +101,7 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                     const uint32_t word = (c & 3) == 0 ? rnd[e][0] : (c & 3) == 1 ? rnd[e][1] : (c & 3) == 2 ? rnd[e][2] : rnd[e][3];
                     fire = (ent.x & 0x100u) && tab.noise_thr_nz && (wide ? ((fire16[e] >> c) & 1u) != 0u : word <= tab.noise_thr_m1);
                 } else if (RNG == GC_RNG_REPLAY) {
-                    if (e < rem && (ent.x & 0x100u)) fire = io.replay[(e0 + e) * C + c] < tab.noise_prob;
+                    if (e < rem && (ent.x & 0x100u)) fire = io.replay[static_cast<size_t>(e0 + e) * C + c] < tab.noise_prob;
                 }
                 const uint32_t nxt = fire ? ((ent.x >> 4) & 15u) : (ent.x & 15u);
                 r[e] += fire ? s_rn[sa_ix] : __uint_as_float(ent.y);          // cell order, from 0.0
@@ -126,12 +127,12 @@ cell_step_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
                 }
             }
             if (io.se_row) {
-                if (c > 0) st_stream_u32(io.se_row + c * ld + e0, sew);
+                if (c > 0) st_stream_u32(io.se_row + (c * ld + e0), sew);
                 if (c == 1 || C == 1) st_stream_u32(io.se_row + e0, sew0);
             }
             const uint32_t out = (row & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c])) & ~keep);
-            st_stream_u32(io.state + c * ld + e0, out);
-            if (io.final_state) st_stream_u32(io.final_state + c * ld + e0, row);
+            st_stream_u32(io.state + (c * ld + e0), out);
+            if (io.final_state) st_stream_u32(io.final_state + (c * ld + e0), row);
             const uint32_t place = tab.place[c];
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) idx[e] += byte_of(out, e) * place;

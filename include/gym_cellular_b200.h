@@ -96,7 +96,8 @@ typedef struct {
                                     > 0 = time-limit truncation with fused auto-reset             */
     uint32_t flags;              /* GC_F_*                                                        */
     int64_t  n_envs;             /* envs of this shard                                            */
-    int64_t  ld;                 /* row stride, >= n_envs, multiple of 16                         */
+    int64_t  ld;                 /* row stride, >= n_envs, multiple of 16; n_cells * ld <= 2^31
+                                    (the kernels index with 32-bit element offsets)               */
     int64_t  env_id_offset;      /* global id of env 0 (multiple of 4): RNG streams are keyed by global env id */
     uint64_t seed;               /* Philox key                                                    */
     double   noise_prob;         /* cellular noise threshold (0.1, cells3resetVdeadlock.py:36)    */
