@@ -43,6 +43,7 @@ int fail(int code, const char *fmt, ...)
 
 constexpr int kHostStreams = 3;
 constexpr int kManyGraphs = 4;
+constexpr int kManyGraphSteps = 32;   // kernels per captured graph: whole passes over the slot list, at least this many steps
 
 // Entry points run on the handle's device but leave the caller's current device untouched (a torch
 // process may be driving several GPUs).
@@ -99,7 +100,7 @@ struct gc_env {
     cudaEvent_t hevent[kHostStreams];
     bool host_ready;
     // gc_step_many: instantiated CUDA graphs of one pass over a slot list (launch-bound batch sizes)
-    struct ManyGraph { int32_t slots[GC_MAX_BINDINGS]; int32_t n_slots; cudaGraphExec_t exec; } many[kManyGraphs];
+    struct ManyGraph { int32_t slots[GC_MAX_BINDINGS]; int32_t n_slots, n_steps; cudaGraphExec_t exec; } many[kManyGraphs];
     int n_many;
 };
 
@@ -591,18 +592,27 @@ int gc_step_bound(gc_env *env, int32_t slot, void *stream)
 namespace {
 // The instantiated graph of one pass over `slots` (one kernel node per bound step, chained by the programmatic
 // dependency edges the launches carry), captured on a stream of the handle; NULL if it cannot be built.
-cudaGraphExec_t many_graph(gc_env *env, const int32_t *slots, int32_t n_slots)
+const gc_env::ManyGraph *many_graph(gc_env *env, const int32_t *slots, int32_t n_slots)
 {
     for (int i = 0; i < env->n_many; ++i)
         if (env->many[i].n_slots == n_slots && std::memcmp(env->many[i].slots, slots, n_slots * sizeof(int32_t)) == 0)
-            return env->many[i].exec;
+            return &env->many[i];
     if (n_slots > GC_MAX_BINDINGS || host_streams(env) != GC_OK) return nullptr;
     if (env->n_many == kManyGraphs) drop_many_graphs(env);
+    // several passes per graph: the gap between two graph launches (~2-3 us on the device) is paid once per
+    // kManyGraphSteps kernels instead of once per n_slots
+    static const int graph_steps = [] {
+        const char *v = std::getenv("GC_B200_STEP_MANY_GRAPH_STEPS");
+        const int k = v ? std::atoi(v) : 0;
+        return k > 0 ? k : kManyGraphSteps;
+    }();
+    const int32_t passes = (graph_steps + n_slots - 1) / n_slots;
     cudaStream_t cap = env->hstream[0];
     const int64_t launches = env->launches, step = env->global_step;      // capturing executes nothing
     if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     int rc = GC_OK;
-    for (int32_t i = 0; i < n_slots && rc == GC_OK; ++i) rc = launch_bound(env, slots[i], cap);
+    for (int32_t p = 0; p < passes && rc == GC_OK; ++p)
+        for (int32_t i = 0; i < n_slots && rc == GC_OK; ++i) rc = launch_bound(env, slots[i], cap);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(cap, &graph);
     env->launches = launches; env->global_step = step;
@@ -613,8 +623,9 @@ cudaGraphExec_t many_graph(gc_env *env, const int32_t *slots, int32_t n_slots)
     gc_env::ManyGraph &m = env->many[env->n_many++];
     std::memcpy(m.slots, slots, n_slots * sizeof(int32_t));
     m.n_slots = n_slots;
+    m.n_steps = passes * n_slots;
     m.exec = exec;
-    return exec;
+    return &m;
 }
 
 // Graph replay pays off where the HOST call per kernel is the bound: short kernels.  Measured (same box, 2000
@@ -656,11 +667,11 @@ int gc_step_many(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t n_s
     cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
     if (many_graphs_enabled(env) && n_slots >= 2 && n_steps >= 2 * n_slots &&
         cudaStreamIsCapturing(st, &capturing) == cudaSuccess && capturing == cudaStreamCaptureStatusNone) {
-        if (cudaGraphExec_t exec = many_graph(env, slots, n_slots)) {
-            for (; done + n_slots <= n_steps; done += n_slots) {
-                GC_CUDA(cudaGraphLaunch(exec, st));
-                env->launches += n_slots;
-                env->global_step += n_slots;
+        if (const gc_env::ManyGraph *m = many_graph(env, slots, n_slots)) {
+            for (; done + m->n_steps <= n_steps; done += m->n_steps) {
+                GC_CUDA(cudaGraphLaunch(m->exec, st));
+                env->launches += m->n_steps;
+                env->global_step += m->n_steps;
             }
         }
     }

@@ -278,6 +278,24 @@ __device__ __forceinline__ void block_flush_stats(const ThreadStats &ts, unsigne
     if (threadIdx.x < 5 && s_stats[threadIdx.x]) atomicAdd(&g_stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
+// Grid world: 'unsafe' is constant 0 (grid_world.py:174-175), the rewards are small integers (a 32-bit sum per
+// thread), and the env-step count of a launch is known before it runs: 6 REDUX instead of 11 at the tail of a
+// kernel that lasts 7 us at 2^20 envs.
+__device__ __forceinline__ void block_flush_stats_grid(uint32_t count, uint32_t truncated, uint32_t reward,
+                                                       unsigned long long launch_steps, unsigned long long *s_stats,
+                                                       unsigned long long *g_stats)
+{
+    const unsigned long long w[3] = {warp_sum(count), warp_sum(truncated), warp_sum(reward) << 24};
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (w[i]) atomicAdd(&s_stats[2 + i], w[i]);
+    }
+    __syncthreads();
+    if (threadIdx.x >= 2 && threadIdx.x < 5 && s_stats[threadIdx.x]) atomicAdd(&g_stats[threadIdx.x], s_stats[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_stats[0], launch_steps);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch: consecutive step kernels of a stream (or of a captured graph) are
 // launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that kernel N+1 becomes resident

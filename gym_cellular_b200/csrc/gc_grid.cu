@@ -97,7 +97,7 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     __syncthreads();
 
     const uint32_t step_counter = step_counter_arrive(io, &s_ctr);
-    uint32_t st_steps = 0, st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
+    uint32_t st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
     for (; e0 < e_end; e0 += stride) {
         const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
@@ -230,7 +230,6 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         const uint32_t iout[kEPT] = {x02 & 0xFFFFu, x13 & 0xFFFFu, x02 >> 16, x13 >> 16};
         {
             const uint32_t vb = valid_bytes(rem);
-            st_steps += rem;
             st_count = add_bytes(count_w & vb, st_count);
             st_trunc = add_bytes(trunc_w & vb, st_trunc);
             st_reward = add_bytes(rew_w & vb, st_reward);
@@ -251,10 +250,8 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
         st_stream_u32(io.count + e0, count_w);
     }
     if (bad_bits & 0x40404040u) atomicOr(io.status, 1ull);
-    if (io.stats) {
-        const ThreadStats ts = {st_steps, 0, st_count, st_trunc, static_cast<long long>(st_reward) << 24};
-        block_flush_stats(ts, s_stats, io.stats);
-    }
+    if (io.stats)
+        block_flush_stats_grid(st_count, st_trunc, st_reward, static_cast<unsigned long long>(io.end - io.begin), s_stats, io.stats);
     step_counter_finish(io, &s_ctr);
 }
 

@@ -279,11 +279,11 @@ def test_step_many_bound_and_graph(B, O):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora)
     assert env.sync_step_counter() == 27
-    env.step_many(slots, 29)                                           # 3 graph replays of the 8-slot pass + 5 plain launches
-    for i in range(29):
+    env.step_many(slots, 70)                               # 2 replays of the cached 32-step graph + 6 plain launches
+    for i in range(70):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora)
-    assert env.sync_step_counter() == 56 and env.launch_count >= 56
+    assert env.sync_step_counter() == 97 and env.launch_count >= 97
 
 
 def test_make_vector_env_layouts_and_debug_ids(B):

@@ -1005,7 +1005,7 @@ def test_final_observation_int8_layout(B, O, kind):
 
 
 def test_step_many_int8_layout(B, O):
-    """gc_step_many on the int8 layout: 19 steps over a ring of 8 bound action buffers in one foreign call,
+    """gc_step_many on the int8 layout: steps over a ring of 8 bound action buffers in one foreign call (plain launches and graph replay),
     grid world (global-step RNG counter, read from device memory by every launch)."""
     n = 20011
     env = B.CellularVectorEnv(kind="gridworld", num_envs=n, env_seed=5, max_episode_steps=7, dispersal_prob=0.1)
@@ -1022,11 +1022,17 @@ def test_step_many_int8_layout(B, O):
         t[:, :n] = dev(a)
         ring.append(t)
     slots = [env._bind(t) for t in ring]
-    env.step_many(slots, 19)
+    env.step_many(slots, 19)                               # plain launches (fewer steps than one cached graph holds)
     for i in range(19):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora, check_se=False)
     assert env.sync_step_counter() == 19
+    env.prepare_step_many(slots)
+    env.step_many(slots, 77)                               # 2 replays of the cached 32-step graph + 13 plain launches
+    for i in range(77):
+        ora.step(acts[i % 8])
+    assert_matches_oracle(env, ora, check_se=False)
+    assert env.sync_step_counter() == 96 and env.stats()["env_steps"] == 96 * n
 
 
 def test_log2_reward_max_relative_error(B, golden_pol):
