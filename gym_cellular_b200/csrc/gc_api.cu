@@ -43,7 +43,7 @@ int fail(int code, const char *fmt, ...)
 
 constexpr int kHostStreams = 3;
 constexpr int kManyGraphs = 4;
-constexpr int kManyGraphSteps = 32;   // kernels per captured graph: whole passes over the slot list, at least this many steps
+constexpr int kManyGraphSteps = 16;   // kernels per captured graph: whole passes over the slot list, at least this many steps
 
 // Entry points run on the handle's device but leave the caller's current device untouched (a torch
 // process may be driving several GPUs).

@@ -195,9 +195,9 @@ int gc_bind_step(gc_env *env, int32_t slot, const int8_t *actions, int8_t *state
 int gc_step_bound(gc_env *env, int32_t slot, void *stream);
 /* n_steps pre-bound steps back to back in ONE foreign call: step i launches slot slots[i % n_slots]
  * (int8 or packed bindings), one kernel per step, chained with programmatic dependent launch; no host code
- * runs between them.  Whole passes over the slot list (32 steps or more per graph) are replayed from a CUDA
+ * runs between them.  Whole passes over the slot list (16 steps or more per graph) are replayed from a CUDA
  * graph the handle captures once per slot list (caller's stream not being captured; GC_B200_STEP_MANY_GRAPH=0
- * in the environment switches it off): the host then pays one call per 32 kernels, which is what bounds the
+ * in the environment switches it off): the host then pays one call per 16 kernels, which is what bounds the
  * launch-bound batch sizes (BASELINE configs 2 and 3).  Same kernels, same results, same statistics.
  * Shards above 2^21 envs always take plain launches (their kernels are long enough to hide the host calls).
  * gc_prepare_step_many builds the graph of a slot list ahead of time (no step is executed), so that the first

@@ -279,7 +279,7 @@ def test_step_many_bound_and_graph(B, O):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora)
     assert env.sync_step_counter() == 27
-    env.step_many(slots, 70)                               # 2 replays of the cached 32-step graph + 6 plain launches
+    env.step_many(slots, 70)                               # 4 replays of the cached 16-step graph + 6 plain launches
     for i in range(70):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora)

@@ -1028,7 +1028,7 @@ def test_step_many_int8_layout(B, O):
     assert_matches_oracle(env, ora, check_se=False)
     assert env.sync_step_counter() == 19
     env.prepare_step_many(slots)
-    env.step_many(slots, 77)                               # 2 replays of the cached 32-step graph + 13 plain launches
+    env.step_many(slots, 77)                               # 4 replays of the cached 16-step graph + 13 plain launches
     for i in range(77):
         ora.step(acts[i % 8])
     assert_matches_oracle(env, ora, check_se=False)
