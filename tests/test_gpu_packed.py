@@ -302,3 +302,22 @@ def test_make_vector_env_layouts_and_debug_ids(B):
         B.make_vector_env("gym_cellular/GridWorld-v0", 64, layout="packed")
     with pytest.raises(ValueError):
         B.PackedCellularVectorEnv(num_envs=16, n_cells=4, n_states=5)
+
+
+def test_example_packed_tabular_agent(B):
+    """examples/packed_tabular_agent.py: a tabular agent consuming index / reward / flag of the packed env learns
+    to avoid the unsafe states; the env's own statistics agree with what the agent saw."""
+    import importlib.util
+    import sys
+    from conftest import REPO
+    spec = importlib.util.spec_from_file_location("packed_tabular_agent", REPO + "/examples/packed_tabular_agent.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv, sys.argv = sys.argv, ["x", "--envs", "8192", "--steps", "240"]
+    try:
+        res = mod.main()
+    finally:
+        sys.argv = argv
+    assert res["env_steps"] == 8192 * 240 and res["kernel_launches"] >= 240
+    assert abs(res["stats_reward_sum"] - res["total_reward"]) <= 1e-3 * abs(res["total_reward"])
+    assert res["unsafe_rate_last_quarter"] < 0.5 * max(res["unsafe_rate"], 1e-9) or res["unsafe_rate_last_quarter"] < 0.01
