@@ -24,7 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--unsafe-penalty", type=float, default=1.0)
+    ap.add_argument("--unsafe-penalty", type=float, default=2.0)
     args = ap.parse_args()
     n, C, S, A = args.envs, 3, 3, 3
     env = gcb.PackedCellularVectorEnv(num_envs=n, n_cells=C, n_states=S, stochastic=True, env_seed=1, difficulty="easy")

@@ -53,8 +53,8 @@ class PackedCellularVectorEnv(CellularVectorEnv):
     """
 
     def __init__(self, *args, emit_side_effects=False, **kwargs):
-        kwargs.setdefault("kind", "cellular")
-        if kwargs["kind"] != "cellular":
+        kind = args[0] if args else kwargs.setdefault("kind", "cellular")
+        if kind != "cellular":
             raise ValueError("the packed layout covers the cellular (polarisation) family")
         super().__init__(*args, emit_side_effects=emit_side_effects, **kwargs)
 
@@ -339,6 +339,9 @@ class PackedCellularVectorEnv(CellularVectorEnv):
         return self._host_np["actions"][:self.num_envs].view(np.uint32)
 
     def _step_host(self, actions):
+        if self._final is not None or self._se_row is not None:
+            raise NotImplementedError("the host path of the packed layout returns state words, rewards and flags; "
+                                      "final observations and side-effect rows are device-path outputs")
         if self._host is None:
             self._alloc_host()
         n, h = self.num_envs, self._host_np

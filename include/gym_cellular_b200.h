@@ -247,7 +247,8 @@ int gc_bind_step_packed(gc_env *env, int32_t slot, const uint32_t *actions, uint
                         float *reward, uint32_t *index, uint8_t *flags, uint32_t *final_state, uint32_t *se_row,
                         int64_t *stats);
 /* Host caller, packed wire format: h_actions in (4 bytes per env), h_state / h_reward / h_flags (and h_index
- * when asked for) out; chunks pipelined over the handle's streams like gc_step_host. */
+ * when asked for) out; chunks pipelined over the handle's streams like gc_step_host.  (final_state and se_row
+ * are outputs of the device path only.) */
 int gc_step_host_packed(gc_env *env, const uint32_t *h_actions, uint32_t *h_state, float *h_reward,
                         uint32_t *h_index, uint8_t *h_flags, uint32_t *d_actions, uint32_t *d_state, int32_t *d_t,
                         float *d_reward, uint32_t *d_index, uint8_t *d_flags, int64_t *d_stats, int64_t chunk_envs);
