@@ -240,6 +240,11 @@ def time_device_path(batches, steps, warmup, dist, device, sampler_index, reduce
             # up to milliseconds apart, and with a collective inside the region every rank would pay for that skew
             # at the first reduction (8 GPUs, 200 steps: 218.8 instead of 195 us per step)
             dist.all_reduce(torch.zeros(1, device=device))
+        else:
+            # one rank: a ~100 us spin kernel plays the same role -- the start event and the first step launches are
+            # queued behind it, so the region starts with the first step kernel already in the queue instead of with
+            # the host latency of issuing it (20-50 us of Python: 1-2 % of a 20-step region)
+            torch.cuda._sleep(200_000)
         start.record(main)
         t0 = time.perf_counter()
         run(warmup, warmup + steps)
