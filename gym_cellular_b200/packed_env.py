@@ -271,7 +271,28 @@ class PackedCellularVectorEnv(CellularVectorEnv):
         return launch
 
     def rollout(self, n_steps, policy=None):
-        raise NotImplementedError("the fused rollout kernel works on the int8 layout (CellularVectorEnv.rollout)")
+        """Fused K-step rollout (see `CellularVectorEnv.rollout`).  The rollout kernel keeps the per-cell levels in
+        registers, so the packed state is unpacked for it and packed again afterwards (two extra launches per
+        call, amortised over `n_steps` steps)."""
+        n = self.num_envs
+        if getattr(self, "_ro_ret", None) is None:
+            self._ro_ret = torch.zeros(self.ld, dtype=torch.float32, device=self.device)
+            self._ro_unsafe = torch.zeros(self.ld, dtype=torch.int32, device=self.device)
+            self._ro_index = torch.zeros(self.ld, dtype=torch.int32, device=self.device)
+        kind, ptab = _lib.POLICY_RANDOM, None
+        if policy is not None:
+            ptab = torch.as_tensor(policy, device=self.device).to(torch.int32).contiguous()
+            if ptab.numel() != self.n_states ** self.n_cells:
+                raise ValueError("policy must have one entry per tabular state")
+            kind = _lib.POLICY_TABLE
+        cells = self.unpack(self._state).contiguous()            # int8 [n_cells, ld]
+        _lib.check(self._lib.gc_rollout(self._h, int(n_steps), kind, _ptr(ptab), _ptr(cells), _ptr(self._t),
+                                        _ptr(self._ro_index), _ptr(self._ro_ret), _ptr(self._ro_unsafe), _ptr(self._stats),
+                                        self._stream()))
+        self._state.copy_(self.pack(cells))
+        if self._index is not self._state:
+            self._index.copy_(self._ro_index)
+        return self._ro_ret[:n], self._ro_unsafe[:n]
 
     # ---- views ---------------------------------------------------------------------------------------
     def _lazy_truncated(self):
@@ -340,8 +361,7 @@ class PackedCellularVectorEnv(CellularVectorEnv):
 
     def _step_host(self, actions):
         if self._final is not None or self._se_row is not None:
-            raise NotImplementedError("the host path of the packed layout returns state words, rewards and flags; "
-                                      "final observations and side-effect rows are device-path outputs")
+            return self._step_host_extras(actions)
         if self._host is None:
             self._alloc_host()
         n, h = self.num_envs, self._host_np
@@ -374,6 +394,34 @@ class PackedCellularVectorEnv(CellularVectorEnv):
             self._h_false = np.zeros(n, np.bool_)
         trunc = (flags & _lib.FLAG_TRUNCATED).astype(np.bool_) if self.max_episode_steps else self._h_false
         return state, h["reward"][:n], self._h_false, trunc, infos
+
+
+def _step_host_extras(self, actions):
+    """Host path when final observations or side-effect rows were asked for: those are outputs of the device path
+    (`gc_step_host_packed` carries state words, rewards and flags only), so the step is taken there and the
+    arrays are copied to the host one by one -- correct, not pipelined."""
+    n = self.num_envs
+    if isinstance(actions, (tuple, list)):
+        actions = np.stack(actions)
+    if actions.ndim == 2:
+        if actions.shape == (n, self.n_cells) and n != self.n_cells:
+            actions = actions.T
+        actions = pack_host(actions)
+    self.step_device(torch.from_numpy(np.ascontiguousarray(actions).astype(np.uint32, copy=False).view(np.int32)).to(self.device))
+    flags = self._flags[:n].cpu().numpy()
+    state = self._state[:n].cpu().numpy().view(np.uint32)
+    infos = _HostInfos(flags, state, self._index[:n].cpu().numpy().view(np.uint32), self.n_cells)
+    if self._final is not None:
+        infos["final_obs"] = self._final[:n].cpu().numpy().view(np.uint32)
+        infos["_final_obs"] = (flags & _lib.FLAG_TRUNCATED).astype(np.bool_)
+    if self._se_row is not None:
+        infos["side_effects_packed"] = self._se_row[:n].cpu().numpy().view(np.uint32)
+    false = np.zeros(n, np.bool_)
+    trunc = (flags & _lib.FLAG_TRUNCATED).astype(np.bool_) if self.max_episode_steps else false
+    return state, self._reward[:n].cpu().numpy(), false, trunc, infos
+
+
+PackedCellularVectorEnv._step_host_extras = _step_host_extras
 
 
 class _HostInfos(dict):

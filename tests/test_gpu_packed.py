@@ -247,6 +247,51 @@ def test_host_path_packed(B, O):
     assert_matches_oracle(env, ora)
 
 
+def test_host_path_with_final_obs_and_side_effect_rows(B, O):
+    """A host-path step of an env that emits final observations / side-effect rows (the un-pipelined branch)."""
+    n = 5003
+    env = B.PackedCellularVectorEnv(num_envs=n, n_cells=5, n_states=3, stochastic=True, env_seed=8, max_episode_steps=3,
+                                    emit_final_obs=True, emit_side_effects=True)
+    lim = O.OracleEnv(n_envs=n, n_cells=5, n_states=3, noise=True, rng_episodic=True, seed=8, max_episode_steps=3,
+                      reward="nonlinear_rp")
+    ora = O.OracleEnv(n_envs=n, n_cells=5, n_states=3, noise=True, rng_episodic=True, seed=8, reward="nonlinear_rp")
+    rng = np.random.default_rng(8)
+    for t in range(7):
+        a = rng.integers(0, 3, size=(5, n)).astype(np.int8)
+        obs, rew, term, trunc, info = env.step(a if t % 2 else pack(a))
+        ora.state[:] = lim.state
+        ora.t[:] = lim.t
+        ora.step(a)
+        lim.step(a)
+        assert isinstance(obs, np.ndarray) and (obs == pack(lim.state)).all()
+        assert (info["final_obs"] == pack(ora.state)).all() and (info["_final_obs"] == lim.truncated.astype(bool)).all()
+        assert (info["side_effects_packed"] == host(env.side_effects_row()).view(np.uint32)).all()
+        assert (info["unsafe"] == lim.unsafe.astype(bool)).all() and (info["count"] == lim.count).all()
+        assert (trunc == lim.truncated.astype(bool)).all() and not term.any()
+        np.testing.assert_allclose(rew, lim.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+
+
+@pytest.mark.parametrize("C,S,stochastic", [(3, 3, True), (16, 4, True), (7, 2, False)])
+def test_rollout_on_packed_state(B, O, C, S, stochastic):
+    """`rollout` of the packed env (unpack -> fused K-step kernel -> pack) against the oracle's, then ordinary steps."""
+    n = 3001
+    env = B.PackedCellularVectorEnv(num_envs=n, n_cells=C, n_states=S, stochastic=stochastic, env_seed=5, max_episode_steps=7)
+    ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, noise=stochastic, seed=5, rng_episodic=True, max_episode_steps=7,
+                      reward="nonlinear_rp" if stochastic else "right_polarizing")
+    for _ in range(2):
+        ret, uns = env.rollout(9)
+        oret, ouns = ora.rollout(9, None)
+        assert (u32(env.packed_state) == pack(ora.state)).all()
+        assert (host(env.time_step) == ora.t).all() and (host(env.tabular_state()) == ora.index).all()
+        assert (host(uns) == ouns).all()
+        np.testing.assert_allclose(host(ret), oret, rtol=1e-5, atol=1e-6)
+    a = np.random.default_rng(1).integers(0, S, size=(C, n)).astype(np.int8)
+    env.step_device(dev(a))
+    ora.step(a)
+    assert_matches_oracle(env, ora)
+    assert env.stats()["env_steps"] == ora.stats[0] == 19 * n
+
+
 def test_step_many_bound_and_graph(B, O):
     """gc_step_many (n pre-bound steps in one foreign call), bound steps and a captured CUDA graph, in the
     packed layout with non-episodic noise: 3 x 8 distinct steps, all reading the device-resident counter."""
