@@ -206,6 +206,18 @@ void drop_many_graphs(gc_env *env)
     env->n_many = 0;
 }
 
+// A host-path call that fails after it queued copies must not return while they still write the caller's buffers.
+struct HostDrain {
+    gc_env *env;
+    bool done = false;
+    ~HostDrain()
+    {
+        if (done) return;
+        for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(env->hstream[i]);
+        cudaGetLastError();
+    }
+};
+
 int host_streams(gc_env *env)
 {
     if (!env->host_ready) {
@@ -366,8 +378,8 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     const int C = env->cfg.n_cells, S = env->cfg.n_states, A = env->cfg.n_actions;
     const bool noise = (env->cfg.flags & GC_F_NOISE) != 0;
     if (noise && (!t->noisy || !t->draws)) return fail(GC_ERR_INVALID, "GC_F_NOISE needs the noisy and draws tables");
-    drop_many_graphs(env);                     // captured kernel nodes carry the tables by value
-    CellTables &tab = env->tab;
+    // built aside and committed at the end: a rejected call leaves the handle's previous tables in force
+    CellTables tab;
     std::memset(&tab, 0, sizeof(tab));
     for (int s = 0; s < S; ++s)
         for (int a = 0; a < A; ++a) {
@@ -431,11 +443,14 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
 
     // ---- fast path: pair table (gc_cell_fast.cu) -------------------------------------------------
     // (a ragged index needs per-cell place values: generic kernel)
-    env->fast_ok = S <= 4 && A <= 4 && !ragged && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
-    for (int j = 3; j < C && env->fast_ok; ++j)
+    bool fast_ok = S <= 4 && A <= 4 && !ragged && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
+    for (int j = 3; j < C && fast_ok; ++j)
         if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
-            env->fast_ok = false;
-    if (env->fast_ok) {
+            fast_ok = false;
+    // the device copies below are synchronous (pageable source), i.e. ordered after every step launched before
+    // this call on any blocking stream; kernels still in flight on non-blocking streams must be waited for by
+    // the caller (include/gym_cellular_b200.h)
+    if (fast_ok) {
         uint2 lut[GC_PAIR_LUT_ENTRIES];                       // 8.4 KB, on the stack: handles may be set up concurrently
         gc_build_pair_lut(t, C, S, A, noise, lut, &tab.unsafe_rows);
         uint32_t p4 = 1;
@@ -450,11 +465,11 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         GC_CUDA(cudaMemcpy(env->d_packed_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     }
     // ---- 5..8 levels, deterministic: 3-bit pair table (gc_cell_pair8.cu) ---------------------------------
-    env->pair8_ok = !env->fast_ok && S <= 8 && A <= 8 && !ragged && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
-    for (int j = 3; j < C && env->pair8_ok; ++j)
+    bool pair8_ok = !fast_ok && S <= 8 && A <= 8 && !ragged && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
+    for (int j = 3; j < C && pair8_ok; ++j)
         if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
-            env->pair8_ok = false;
-    if (env->pair8_ok) {
+            pair8_ok = false;
+    if (pair8_ok) {
         std::unique_ptr<uint2[]> lut8(new (std::nothrow) uint2[GC_PAIR8_ENTRIES]);
         if (!lut8) return fail(GC_ERR_INVALID, "out of host memory");
         gc_build_pair8_lut(t, C, S, A, lut8.get(), &tab.unsafe_rows8);
@@ -462,6 +477,10 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         if (!env->d_pair8_lut) GC_CUDA(cudaMalloc(&env->d_pair8_lut, GC_PAIR8_ENTRIES * sizeof(uint2)));
         GC_CUDA(cudaMemcpy(env->d_pair8_lut, lut8.get(), GC_PAIR8_ENTRIES * sizeof(uint2), cudaMemcpyHostToDevice));
     }
+    drop_many_graphs(env);                     // captured kernel nodes carry the tables by value
+    env->tab = tab;
+    env->fast_ok = fast_ok;
+    env->pair8_ok = pair8_ok;
     env->tables_set = true;
     return GC_OK;
 }
@@ -693,12 +712,14 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
     if (!h_actions || !d_actions || !d_state || !d_t || !d_reward || !d_index || !d_terminated ||
         !d_truncated || !d_unsafe || !d_count)
         return fail(GC_ERR_INVALID, "a required pointer is NULL");
+    if (h_se_row && !d_se_row) return fail(GC_ERR_INVALID, "h_se_row needs d_se_row");
     GC_ON_DEVICE(env->cfg.device);
     if (int rc = host_streams(env)) return rc;
     const int64_t n = env->cfg.n_envs, ld = env->cfg.ld;
     const int C = env->cfg.n_cells;
     if (chunk_envs <= 0) chunk_envs = 1 << 20;
     chunk_envs = (chunk_envs + 15) / 16 * 16;
+    HostDrain drain{env};
     int k = 0;
     for (int64_t b = 0; b < n; b += chunk_envs, ++k) {
         const int64_t cnt = (b + chunk_envs < n) ? chunk_envs : (n - b);
@@ -715,13 +736,14 @@ int gc_step_host(gc_env *env, const int8_t *h_actions, int8_t *h_state, float *h
         if (h_truncated) GC_CUDA(cudaMemcpyAsync(h_truncated + b, d_truncated + b, cnt, cudaMemcpyDeviceToHost, st));
         if (h_unsafe) GC_CUDA(cudaMemcpyAsync(h_unsafe + b, d_unsafe + b, cnt, cudaMemcpyDeviceToHost, st));
         if (h_count) GC_CUDA(cudaMemcpyAsync(h_count + b, d_count + b, cnt, cudaMemcpyDeviceToHost, st));
-        if (h_se_row && d_se_row)
+        if (h_se_row)
             GC_CUDA(cudaMemcpy2DAsync(h_se_row + b, ld, d_se_row + b, ld, cnt, C, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < kHostStreams && i < k; ++i) GC_CUDA(cudaStreamSynchronize(env->hstream[i]));
     // every chunk read the device-resident global step; advance it once, after all of them
     if (int rc = tick_global_step(env, env->hstream[0])) return rc;
     GC_CUDA(cudaStreamSynchronize(env->hstream[0]));
+    drain.done = true;
     return GC_OK;
 }
 
@@ -920,6 +942,7 @@ int gc_step_host_packed(gc_env *env, const uint32_t *h_actions, uint32_t *h_stat
     const int64_t n = env->cfg.n_envs;
     if (chunk_envs <= 0) chunk_envs = 1 << 20;
     chunk_envs = (chunk_envs + 15) / 16 * 16;
+    HostDrain drain{env};
     int k = 0;
     for (int64_t b = 0; b < n; b += chunk_envs, ++k) {
         const int64_t cnt = (b + chunk_envs < n) ? chunk_envs : (n - b);
@@ -936,6 +959,7 @@ int gc_step_host_packed(gc_env *env, const uint32_t *h_actions, uint32_t *h_stat
     for (int i = 0; i < kHostStreams && i < k; ++i) GC_CUDA(cudaStreamSynchronize(env->hstream[i]));
     if (int rc = tick_global_step(env, env->hstream[0])) return rc;
     GC_CUDA(cudaStreamSynchronize(env->hstream[0]));
+    drain.done = true;
     return GC_OK;
 }
 

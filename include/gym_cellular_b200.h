@@ -136,7 +136,11 @@ const char *gc_last_error(void);
 
 int gc_create(const gc_config *cfg, gc_env **out);
 int gc_destroy(gc_env *env);
-int gc_set_tables(gc_env *env, const gc_cell_tables *tables);   /* cellular family only */
+/* Cellular family only.  Validates everything first: a rejected call leaves the previous tables in force.  The
+ * staged device tables are replaced with synchronous copies, so steps still in flight on a NON-BLOCKING stream must
+ * be waited for by the caller before the tables are changed; bindings stay valid, cached gc_step_many graphs are
+ * rebuilt on their next use. */
+int gc_set_tables(gc_env *env, const gc_cell_tables *tables);
 
 /* Final observation (gymnasium's SAME_STEP auto-reset convention; the reference never ends an episode,
  * gym_cellular/__init__.py:7, so this belongs to the time limit added here): when set, every following

@@ -807,6 +807,20 @@ def test_argument_errors_on_gpu(B):
         B.CellularVectorEnv(num_envs=16, n_cells=3, n_states=6, stochastic=True).rollout(3)     # fast path only
 
 
+def test_rejected_tables_leave_the_previous_ones_in_force(B, O):
+    """gc_set_tables validates before it commits: after a rejected call the env steps by its old rules."""
+    import ctypes as C
+    from gym_cellular_b200 import _lib
+    n = 1000
+    env = B.CellularVectorEnv(num_envs=n, env_seed=3)
+    ora = O.OracleEnv(n_envs=n, seed=3, rng_episodic=True)
+    move = np.zeros((3, 3), np.int8); move[2, 2] = 3                   # level 3 does not exist
+    ok = [np.zeros((3, 3), np.float32), np.zeros((3, 3, 3), np.int8), np.zeros(3, np.uint8), np.zeros(3, np.int8)]
+    t = _lib.GcCellTables(move.ctypes.data, None, None, *[a.ctypes.data for a in ok], None, None)
+    assert env._lib.gc_set_tables(env._h, C.byref(t)) == _lib.ERR_INVALID and b"outside" in env._lib.gc_last_error()
+    _rollout(env, ora, 6, np.random.default_rng(0))
+
+
 def test_second_device_leaves_current_device_alone(B, O):
     """A handle on cuda:1 runs there without changing the caller's current device."""
     if torch.cuda.device_count() < 2:
