@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libgymcellular_b200.so")
+# GC_B200_LIB_DIR: directory of an alternative in-tree build (A/B runs of tuning variants, gym_cellular_b200/build.py)
+LIB_PATH = os.path.join(os.environ.get("GC_B200_LIB_DIR") or os.path.join(_PKG, "lib"), "libgymcellular_b200.so")
 
 ABI_VERSION = 2
 KIND_CELLULAR, KIND_GRIDWORLD = 0, 1

@@ -45,35 +45,62 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // and the two result bits of a word are gathered with one multiply (bits 15, 31 -> 30, 31).
 // Returns bit c = the draw of cell c fired, for c < 8 * NB (NB Philox blocks).
 
-// the rare part, kept out of line so that its registers (a whole Philox block) do not weigh on the callers
-__device__ __noinline__ uint32_t resolve_noise_ties(uint32_t ties, uint32_t r16, uint32_t gid_lo, uint32_t gid_hi, uint32_t ctr,
-                                                    const uint32_t *rk)
+// The rare part, kept out of line so that its registers do not weigh on the callers: some half of this env ties with
+// the threshold's top half, so its draws are formed again block by block, with the low halves of the tied ones.
+// The round keys are rebuilt from the seed (k + r * W) instead of being read through a pointer: a warp that gets
+// here holds up its whole block, so the path is short even though it is rare (once per ~120 warp iterations).
+__device__ __forceinline__ void philox4x32_10_seeded(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
 {
-    uint32_t fire = 0;
-    do {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = static_cast<unsigned long long>(0xD2511F53u) * c[0];
+        const unsigned long long p1 = static_cast<unsigned long long>(0xCD9E8D57u) * c[2];
+        c[0] = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
+        c[1] = static_cast<uint32_t>(p1);
+        c[2] = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
+        c[3] = static_cast<uint32_t>(p0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __noinline__ uint32_t noise_fire_with_ties(int n_blocks, uint32_t k16, uint32_t r16, uint32_t gid_lo, uint32_t gid_hi,
+                                                      uint32_t ctr, uint32_t seed_lo, uint32_t seed_hi)
+{
+    uint32_t fire = 0, ties = 0;
+#pragma unroll 1
+    for (int b = 0; b < n_blocks; ++b) {
+        uint32_t w[4] = {gid_lo, gid_hi, ctr, static_cast<uint32_t>(b)};
+        philox4x32_10_seeded(w, seed_lo, seed_hi);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const uint32_t half = (h & 1) ? w[h >> 1] >> 16 : w[h >> 1] & 0xFFFFu;
+            if (half < k16) fire |= (1u << h) << (8 * b);
+            if (half == k16) ties |= (1u << h) << (8 * b);
+        }
+    }
+    while (ties) {
         const uint32_t c = static_cast<uint32_t>(__ffs(static_cast<int>(ties))) - 1u;
         ties &= ties - 1u;
-        uint32_t c0 = gid_lo, c1 = gid_hi, c2 = ctr, c3 = GC_NOISE_LOW_STREAM + c;
-#pragma unroll 1
-        for (int r = 0; r < 10; ++r) {
-            const unsigned long long p0 = static_cast<unsigned long long>(0xD2511F53u) * c0;
-            const unsigned long long p1 = static_cast<unsigned long long>(0xCD9E8D57u) * c2;
-            c0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk[2 * r];
-            c1 = static_cast<uint32_t>(p1);
-            c2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
-            c3 = static_cast<uint32_t>(p0);
-        }
-        if ((c0 >> 16) < r16) fire |= 1u << c;
-    } while (ties);
+        uint32_t lo[4] = {gid_lo, gid_hi, ctr, GC_NOISE_LOW_STREAM + c};
+        philox4x32_10_seeded(lo, seed_lo, seed_hi);
+        if ((lo[0] >> 16) < r16) fire |= 1u << c;
+    }
     return fire;
 }
 
+// Ties are detected once per env, not per word: the lane-wise minimum of (half ^ k16) over the block's eight halves
+// (two VIMNMX3.U16x2 per block) has a zero lane iff some half equals k16.  Measured against the per-word
+// equality masks of the first form: 294 -> 284 us per step at 16 cells x 4 levels x 2^24 envs (int8 layout),
+// 207 -> 197 us packed.  Forms that moved the compares onto the FMA pipe (an IMAD for d, one 64-bit multiply-add
+// as the gather, a three-input compare per value of k16's top bit) were measured slower and are not kept
+// (profiles/r02_tuning_log.md).
 template <int NB>
 __device__ __forceinline__ uint32_t fire_bits_wide(const CellTables &tab, uint32_t gid_lo, uint32_t gid_hi, uint32_t ctr,
                                                    const uint32_t (&rk)[20])
 {
     constexpr uint32_t H = 0x80008000u, L = 0x7FFF7FFFu, GATHER = 0x00008001u;
-    uint32_t fire = 0, eq_any = 0, eq[NB][4];
+    uint32_t zmin = 0xFFFFFFFFu, fire = 0;
 #pragma unroll
     for (int b = NB - 1; b >= 0; --b) {
         uint32_t w[4];
@@ -83,20 +110,13 @@ __device__ __forceinline__ uint32_t fire_bits_wide(const CellTables &tab, uint32
             const uint32_t x = w[i];
             const uint32_t d = (x | H) - tab.noise_kk15;
             const uint32_t lt = ~((x & d) | ((x | d) & ~tab.noise_kmask)) & H;
-            const uint32_t z = x ^ tab.noise_kk;
-            eq[b][i] = ~(((z & L) + L) | z) & H;
-            eq_any |= eq[b][i];
             fire = __funnelshift_l(lt * GATHER, fire, 2);
         }
+        zmin = __vimin3_u16x2(zmin, w[0] ^ tab.noise_kk, w[1] ^ tab.noise_kk);
+        zmin = __vimin3_u16x2(zmin, w[2] ^ tab.noise_kk, w[3] ^ tab.noise_kk);
     }
-    if (eq_any) {                                     // rare: a half ties with the threshold's top half
-        uint32_t ties = 0;
-#pragma unroll
-        for (int b = NB - 1; b >= 0; --b)
-#pragma unroll
-            for (int i = 3; i >= 0; --i) ties = __funnelshift_l(eq[b][i] * GATHER, ties, 2);
-        fire |= resolve_noise_ties(ties, tab.noise_r16, gid_lo, gid_hi, ctr, rk);
-    }
+    if (~(((zmin & L) + L) | zmin) & H)               // rare (2^-16 per cell): a half ties with the threshold's top half
+        fire = noise_fire_with_ties(NB, tab.noise_kk & 0xFFFFu, tab.noise_r16, gid_lo, gid_hi, ctr, rk[0], rk[1]);
     return fire;
 }
 

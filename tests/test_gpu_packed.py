@@ -265,7 +265,7 @@ def test_host_path_with_final_obs_and_side_effect_rows(B, O):
         lim.step(a)
         assert isinstance(obs, np.ndarray) and (obs == pack(lim.state)).all()
         assert (info["final_obs"] == pack(ora.state)).all() and (info["_final_obs"] == lim.truncated.astype(bool)).all()
-        assert (info["side_effects_packed"] == host(env.side_effects_row()).view(np.uint32)).all()
+        assert (info["side_effects_packed"] == pack(lim.se_row)).all() and (host(env.side_effects_row()) == lim.se_row).all()
         assert (info["unsafe"] == lim.unsafe.astype(bool)).all() and (info["count"] == lim.count).all()
         assert (trunc == lim.truncated.astype(bool)).all() and not term.any()
         np.testing.assert_allclose(rew, lim.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)
