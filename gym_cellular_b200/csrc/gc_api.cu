@@ -89,7 +89,7 @@ struct gc_env {
     uint32_t *d_done;               // block-arrival counter of the step kernels
     uint2 *d_pair_lut;            // fast-path table (GC_PAIR_LUT_ENTRIES), device memory owned by the handle
     uint2 *d_packed_lut;          // the same rules in the packed layout's index order (gc_cell_packed.cu)
-    uint2 *d_pair8_lut;           // 5..8 levels, deterministic (gc_cell_pair8.cu): GC_PAIR8_ENTRIES entries
+    uint2 *d_pair8_lut;           // 5..8 levels (gc_cell_pair8.cu): GC_PAIR8_ENTRIES entries
     bool pair8_ok;
     int8_t *final_state;          // gc_set_final_obs: optional extra output of every int8-layout step
     bool fast_ok;
@@ -255,8 +255,8 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
             e = gc_launch_cell_tma_step(env->tab, io, env->d_pair_lut, env->n_sm, st);
         else if (env->fast_ok)
             e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, mode, env->n_sm, st);
-        else if (env->pair8_ok && mode == GC_RNG_NONE && !io.se_row)
-            e = gc_launch_cell_pair8_step(env->tab, io, env->d_pair8_lut, env->n_sm, st);
+        else if (env->pair8_ok && mode != GC_RNG_REPLAY && !io.se_row)
+            e = gc_launch_cell_pair8_step(env->tab, io, env->d_pair8_lut, mode, env->n_sm, st);
         else
             e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);
     } else {
@@ -464,7 +464,7 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
         if (!env->d_packed_lut) GC_CUDA(cudaMalloc(&env->d_packed_lut, sizeof(lut)));
         GC_CUDA(cudaMemcpy(env->d_packed_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     }
-    // ---- 5..8 levels, deterministic: 3-bit pair table (gc_cell_pair8.cu) ---------------------------------
+    // ---- 5..8 levels: 3-bit pair table, single-cell table with the fire bit (gc_cell_pair8.cu) -----------
     bool pair8_ok = !fast_ok && S <= 8 && A <= 8 && !ragged && !(env->cfg.flags & GC_F_GENERIC_KERNEL);
     for (int j = 3; j < C && pair8_ok; ++j)
         if (std::memcmp(t->side_effects + (size_t)j * S * S, t->side_effects + (size_t)2 * S * S, (size_t)S * S) != 0)
@@ -472,7 +472,7 @@ int gc_set_tables(gc_env *env, const gc_cell_tables *t)
     if (pair8_ok) {
         std::unique_ptr<uint2[]> lut8(new (std::nothrow) uint2[GC_PAIR8_ENTRIES]);
         if (!lut8) return fail(GC_ERR_INVALID, "out of host memory");
-        gc_build_pair8_lut(t, C, S, A, lut8.get(), &tab.unsafe_rows8);
+        gc_build_pair8_lut(t, C, S, A, noise, lut8.get(), &tab.unsafe_rows8, &tab.unsafe01_rows8);
         GC_ON_DEVICE(env->cfg.device);
         if (!env->d_pair8_lut) GC_CUDA(cudaMalloc(&env->d_pair8_lut, GC_PAIR8_ENTRIES * sizeof(uint2)));
         GC_CUDA(cudaMemcpy(env->d_pair8_lut, lut8.get(), GC_PAIR8_ENTRIES * sizeof(uint2), cudaMemcpyHostToDevice));

@@ -1,5 +1,5 @@
-// Deterministic cellular step for 5..8 levels / actions per cell (int8 layout): the pair-table idea of
-// gc_cell_fast.cu with 3-bit digits.
+// Cellular step for 5..8 levels / actions per cell (int8 layout): the pair-table idea of gc_cell_fast.cu with
+// 3-bit digits.
 //
 // The (level, action) digits of a cell pair (s_c, a_c, s_d, a_d) form a 12-bit index into a 4096-entry table
 // staged in shared memory (32 KB; built on the host by gc_build_pair8_lut from the same [S][A] tables,
@@ -14,7 +14,15 @@
 // A 12-bit index does not fit the byte lanes the 2-bit kernel uses, so the four envs of a thread travel as two
 // 16-bit-lane words (envs 0, 2 and envs 1, 3).  The generic per-cell kernel (gc_kernels.cu) did ~40 instructions
 // per (env, cell) for these shapes and ran at 0.47-0.49 of the HBM roofline (10 cells x 8 levels).
-// Stochastic envs, per-cell side-effect rows on request and ragged radices stay with the generic kernel.
+//
+// Stochastic envs (RNG == GC_RNG_PHILOX; cells3resetVdeadlock.py:35-61 generalised): two fire bits on top of a
+// 12-bit pair index would need a 128 KB table, so the cells are looked up ONE at a time in a 128-entry table
+// [fire][a][s] (same entry layout, cell d empty), and the 'unsafe' flag of the pair (cell 0, cell 1) comes from a
+// 64-bit mask over (s'_0, s'_1) instead of the pair entry.  The draws are those of every other kernel: one 32-bit
+// Philox word per cell up to GC_NARROW_CELLS cells, 16-bit halves with the exact tie rule beyond (fire_bits_wide).
+// The generic kernel ran these shapes at 0.22 of the HBM roofline (10 cells x 8 levels with noise, 570 us per step
+// of 2^24 envs).
+// Replayed draws, per-cell side-effect rows on request and ragged radices stay with the generic kernel.
 #include "gc_device.cuh"
 
 namespace {
@@ -23,11 +31,17 @@ namespace {
 #define GC_PAIR8_MINB 4
 #endif
 
-__global__ void __launch_bounds__(kThreads, GC_PAIR8_MINB)
+template <int RNG>
+#ifndef GC_PAIR8_NOISE_MINB
+#define GC_PAIR8_NOISE_MINB 4        // 64 registers (16 bytes spilled): 311 us against 317 us at three blocks, 10 x 8 with noise
+#endif
+__global__ void __launch_bounds__(kThreads, RNG == GC_RNG_NONE ? GC_PAIR8_MINB : GC_PAIR8_NOISE_MINB)
 cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ StepIO io, const uint2 *__restrict__ lut)
 {
-    __shared__ uint2 s_pair[GC_PAIR8_PAIRS];
-    __shared__ uint2 s_single[64];
+    constexpr bool NOISE = RNG == GC_RNG_PHILOX;
+    constexpr int N_SINGLE = NOISE ? 128 : 64;
+    __shared__ uint2 s_pair[NOISE ? 1 : GC_PAIR8_PAIRS];
+    __shared__ uint2 s_single[N_SINGLE];
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const int C = tab.n_cells;
@@ -36,14 +50,15 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
     const uint32_t stride = gridDim.x * kThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
     uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kThreads + threadIdx.x) * kEPT;
 
-    for (int i = threadIdx.x; i < GC_PAIR8_PAIRS; i += kThreads) s_pair[i] = lut[i];
-    if (threadIdx.x < 64) s_single[threadIdx.x] = lut[GC_PAIR8_PAIRS + threadIdx.x];
+    if constexpr (!NOISE)
+        for (int i = threadIdx.x; i < GC_PAIR8_PAIRS; i += kThreads) s_pair[i] = lut[i];
+    if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR8_PAIRS + threadIdx.x];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     pdl_launch_dependents();
     pdl_wait();
     step_counter_read(io, &s_ctr);
     __syncthreads();
-    step_counter_arrive(io, &s_ctr);
+    [[maybe_unused]] const uint32_t step_counter = step_counter_arrive(io, &s_ctr);
 
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
     long long st_reward = 0;
@@ -68,19 +83,40 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
         uint32_t sum01 = 0, sum23 = 0;          // info low halves of envs (0, 1) and (2, 3) in 16-bit lanes: count in bits 0-4
         uint32_t or01 = 0, or23 = 0;            // bits 8-15 of a lane: levels present in the cells j >= 2; bit 7: pair (0, 1) flag
         uint32_t s0w = 0;                       // next level of cell 0, byte lane e = env e
+        [[maybe_unused]] uint32_t s1w = 0;      // next level of cell 1 (stochastic variant)
+        // fire[e]: bit c = the noise draw of cell c of env e fired (the table ignores it where (level, action)
+        // consumes no draw)
+        [[maybe_unused]] uint32_t fire[kEPT] = {0, 0, 0, 0};
+        if constexpr (NOISE) {
+            const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
+            const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
+            const int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter;
+                if (C > GC_NARROW_CELLS) {
+                    fire[e] = fire_bits_wide<2>(tab, gid_lo | e, gid_hi, ctr, io.round_key);
+                } else {
+                    uint32_t w[4];
+                    philox4x32_10(gid_lo | e, gid_hi, ctr, 0u, io.round_key, w);
+                    const uint32_t thr = tab.noise_thr_m1;    // threshold - 1; a zero threshold never gets here (gc_api.cu)
+                    fire[e] = (w[0] <= thr ? 1u : 0u) | (w[1] <= thr ? 2u : 0u) | (w[2] <= thr ? 4u : 0u) | (w[3] <= thr ? 8u : 0u);
+                }
+            }
+        }
 
         // bookkeeping shared by a pair and a single cell: info low halves, next-state rows of cell c (and d)
-        auto account = [&](const uint2 (&ent)[kEPT], int c, bool pair, bool first) {
+        auto account = [&](const uint2 (&ent)[kEPT], int c, bool pair, uint32_t keep_bits) {
 #pragma unroll
             for (int e = 0; e < kEPT; ++e) r[e] += __uint_as_float(ent[e].y);       // cell order, from 0.0
             const uint32_t w01 = prmt(ent[0].x, ent[1].x, 0x5410), w23 = prmt(ent[2].x, ent[3].x, 0x5410);
             sum01 += w01 & 0x001F001Fu; sum23 += w23 & 0x001F001Fu;
-            const uint32_t keep_bits = first ? 0x00800080u : 0xFF00FF00u;
             or01 |= w01 & keep_bits; or23 |= w23 & keep_bits;
             // SoA rows of the next state: byte 2 (cell c) and byte 3 (cell d) of the four info words
             const uint32_t u = prmt(ent[0].x, ent[1].x, 0x7362), v = prmt(ent[2].x, ent[3].x, 0x7362);
             const uint32_t row_c = prmt(u, v, 0x5410), row_d = prmt(u, v, 0x7632);
-            if (first) s0w = row_c;
+            if (c == 0) s0w = row_c;
+            if (NOISE && c == 1) s1w = row_c;
             const uint32_t out_c = (row_c & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c])) & ~keep);
             st_stream_u32(io.state + (c * ld + e0), out_c);
             if (io.final_state) st_stream_u32(io.final_state + (c * ld + e0), row_c);
@@ -107,12 +143,20 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
                 const uint32_t p13 = ((code_c >> 8) & 0x00FF00FFu) + ((code_d >> 8) & 0x00FF00FFu) * 64u;
                 ent[0] = s_pair[p02 & 0xFFFu]; ent[2] = s_pair[(p02 >> 16) & 0xFFFu];
                 ent[1] = s_pair[p13 & 0xFFFu]; ent[3] = s_pair[(p13 >> 16) & 0xFFFu];
-                account(ent, c, true, c == 0);
+                account(ent, c, true, c == 0 ? 0x00800080u : 0xFF00FF00u);
             } else {
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e) ent[e] = s_single[byte_of(code_c, e) & 63u];
-                account(ent, c, false, c == 0);
+                account(ent, c, false, c == 0 ? 0x00800080u : 0xFF00FF00u);
             }
+        };
+        // stochastic variant: cell c (row i of the current group) alone, its fire bit on top of the 6-bit code
+        auto do_single = [&](int c, int i) {
+            const uint32_t code = (aw[i] & 0x07070707u) * 8u + (sw[i] & 0x07070707u);
+            uint2 ent[kEPT];
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) ent[e] = s_single[(byte_of(code, e) & 63u) | (((fire[e] >> c) & 1u) << 6)];
+            account(ent, c, false, c >= 2 ? 0xFF00FF00u : 0u);
         };
 
         // four cells (two lookups per env) per iteration; the rows of the next four are requested before these are
@@ -126,8 +170,14 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
                     ns[i] = ld_stream_u32(io.state + ((c + 4 + i) * ld + e0));
                     na[i] = ld_stream_u32(io.actions + ((c + 4 + i) * ld + e0));
                 }
-            do_pair(c, 0);
-            if (c + 2 < C) do_pair(c + 2, 2);
+            if constexpr (NOISE) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c + i < C) do_single(c + i, i);
+            } else {
+                do_pair(c, 0);
+                if (c + 2 < C) do_pair(c + 2, 2);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) { sw[i] = ns[i]; aw[i] = na[i]; }
         }
@@ -135,10 +185,13 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
         // unsafe / count per env: the unsafe-levels mask of s'_0 against the levels present in the cells j >= 2
         const uint32_t count_w = prmt(sum01, sum23, 0x6420) & 0x1F1F1F1Fu;
         const uint32_t present = prmt(or01, or23, 0x7531);                 // byte e: levels present in cells j >= 2 of env e
-        const uint32_t flag01 = (prmt(or01, or23, 0x6420) >> 7) & 0x01010101u;
-        uint32_t unsafe_w = flag01;
+        uint32_t unsafe_w = NOISE ? 0u : (prmt(or01, or23, 0x6420) >> 7) & 0x01010101u;
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) {
+            if constexpr (NOISE) {      // entries 0 and 1 of row 0 of the side-effects matrix, from (s'_0, s'_1) (s'_0 twice if C == 1)
+                const uint32_t s1n = byte_of(C >= 2 ? s1w : s0w, e) & 7u;
+                unsafe_w |= (static_cast<uint32_t>(tab.unsafe01_rows8 >> (8u * (byte_of(s0w, e) & 7u) + s1n)) & 1u) << (8 * e);
+            }
             const uint32_t rowmask = static_cast<uint32_t>(tab.unsafe_rows8 >> (8u * (byte_of(s0w, e) & 7u))) & 0xFFu;
             unsafe_w |= ((byte_of(present, e) & rowmask) ? 1u : 0u) << (8 * e);
         }
@@ -172,8 +225,13 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
 
 }  // namespace
 
-cudaError_t gc_launch_cell_pair8_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm, cudaStream_t st)
+cudaError_t gc_launch_cell_pair8_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode, int n_sm,
+                                      cudaStream_t st)
 {
     const int64_t n = io.end - io.begin;
-    return launch_step_kernel(cell_pair8_kernel, grid_for<cell_pair8_kernel>(n, n_sm), kThreads, 0, st, tab, io, lut);
+    if (rng_mode == GC_RNG_PHILOX)
+        return launch_step_kernel(cell_pair8_kernel<GC_RNG_PHILOX>, grid_for<cell_pair8_kernel<GC_RNG_PHILOX>>(n, n_sm), kThreads, 0,
+                                  st, tab, io, lut);
+    return launch_step_kernel(cell_pair8_kernel<GC_RNG_NONE>, grid_for<cell_pair8_kernel<GC_RNG_NONE>>(n, n_sm), kThreads, 0, st,
+                              tab, io, lut);
 }

@@ -111,6 +111,8 @@ struct CellTables {
     uint32_t init_packed;            // initial state, 2 bits per cell
     // 5..8 levels (gc_cell_pair8.cu): byte s0' = set of levels x with SE[j >= 2][s0'][x] == unsafe
     unsigned long long unsafe_rows8;
+    // stochastic variant: bit 8 s0' + s1' = entry 0 or 1 of row 0 of the side-effects matrix is 'unsafe' for (s0', s1')
+    unsigned long long unsafe01_rows8;
 };
 
 struct GridParams {
@@ -144,12 +146,14 @@ cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, co
 // TMA bulk-staged variant of the deterministic pair-table step for wide envs (gc_cell_tma.cu)
 cudaError_t gc_launch_cell_tma_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
                                     cudaStream_t stream);
-// 5..8 levels / actions, deterministic (gc_cell_pair8.cu): 4096 pair entries [a_d][s_d][a_c][s_c] (3-bit digits)
-// followed by 64 single-cell entries [a][s]
+// 5..8 levels / actions (gc_cell_pair8.cu): 4096 pair entries [a_d][s_d][a_c][s_c] (3-bit digits, no noise)
+// followed by 128 single-cell entries [fire][a][s]
 #define GC_PAIR8_PAIRS 4096
-#define GC_PAIR8_ENTRIES (GC_PAIR8_PAIRS + 64)
-void gc_build_pair8_lut(const gc_cell_tables *t, int C, int S, int A, uint2 *lut, unsigned long long *unsafe_rows8);
-cudaError_t gc_launch_cell_pair8_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm, cudaStream_t stream);
+#define GC_PAIR8_ENTRIES (GC_PAIR8_PAIRS + 128)
+void gc_build_pair8_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut, unsigned long long *unsafe_rows8,
+                        unsigned long long *unsafe01_rows8);
+cudaError_t gc_launch_cell_pair8_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode, int n_sm,
+                                      cudaStream_t stream);
 // packed layout: lut = GC_PAIR_LUT_ENTRIES entries in the packed index order (gc_build_packed_lut)
 void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut);
 cudaError_t gc_launch_cell_packed_step(const CellTables &tab, const PackedIO &io, const uint2 *lut, bool noise,

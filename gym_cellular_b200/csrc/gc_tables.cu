@@ -149,30 +149,40 @@ void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool nois
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cellular family, 5..8 levels / actions, deterministic (gc_cell_pair8.cu): the pair entries of gc_build_pair_lut
-// with 3-bit digits.  pair index p = s_c | a_c << 3 | s_d << 6 | a_d << 9, single index p = s | a << 3.
+// Cellular family, 5..8 levels / actions (gc_cell_pair8.cu): the pair entries of gc_build_pair_lut with 3-bit
+// digits (no noise: deterministic launches only), then the single-cell entries with the fire bit on top.
+// pair index p = s_c | a_c << 3 | s_d << 6 | a_d << 9, single index p = s | a << 3 | fire << 6.
 //   .x  bits 0-4 counted next levels, bit 7 pair-(0, 1) 'unsafe' flag, bits 8-15 one-hot set of the next levels,
 //       bits 16-23 next level of cell c, bits 24-31 next level of cell d;  .y reward contribution (float)
-void gc_build_pair8_lut(const gc_cell_tables *t, int C, int S, int A, uint2 *lut, unsigned long long *unsafe_rows8)
+void gc_build_pair8_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut, unsigned long long *unsafe_rows8,
+                        unsigned long long *unsafe01_rows8)
 {
     auto ok = [&](int s, int a) { return s < S && a < A; };
-    auto nxt = [&](int s, int a) { return ok(s, a) ? (int)t->move[s * A + a] : 0; };
-    auto rw = [&](int s, int a) { return ok(s, a) ? (double)t->reward[s * A + a] : 0.0; };
+    auto nxt = [&](int s, int a, int fire) {
+        if (!ok(s, a)) return 0;
+        if (noise && fire && t->draws[s * A + a]) return (int)t->noisy[s * A + a];
+        return (int)t->move[s * A + a];
+    };
+    auto rw = [&](int s, int a, int fire) {
+        if (!ok(s, a)) return 0.0;
+        if (noise && fire && t->draws[s * A + a] && t->reward_noisy) return (double)t->reward_noisy[s * A + a];
+        return (double)t->reward[s * A + a];
+    };
     auto se = [&](int j, int s0, int sp) { return (int)t->side_effects[((size_t)j * S + s0) * S + sp]; };
     auto cn = [&](int n) { return t->counted[n] ? 1u : 0u; };
     for (int p = 0; p < GC_PAIR8_PAIRS; ++p) {
         const int sc = p & 7, ac = (p >> 3) & 7, sd = (p >> 6) & 7, ad = (p >> 9) & 7;
-        const int nc = nxt(sc, ac), nd = nxt(sd, ad);
+        const int nc = nxt(sc, ac, 0), nd = nxt(sd, ad, 0);
         const uint32_t uns01 = (C >= 2 && (se(0, nc, nd) == 2 || se(1, nc, nd) == 2)) ? 1u : 0u;
         lut[p].x = (cn(nc) + cn(nd)) | (uns01 << 7) | (((1u << nc) | (1u << nd)) << 8) | ((uint32_t)nc << 16) | ((uint32_t)nd << 24);
-        const float f = (float)(rw(sc, ac) + rw(sd, ad));
+        const float f = (float)(rw(sc, ac, 0) + rw(sd, ad, 0));
         std::memcpy(&lut[p].y, &f, sizeof(f));
     }
-    for (int p = 0; p < 64; ++p) {
-        const int s = p & 7, a = (p >> 3) & 7, n = nxt(s, a);
+    for (int p = 0; p < 128; ++p) {
+        const int s = p & 7, a = (p >> 3) & 7, n = nxt(s, a, p >> 6);
         const uint32_t uns0 = (C == 1 && se(0, n, n) == 2) ? 1u : 0u;
         lut[GC_PAIR8_PAIRS + p].x = cn(n) | (uns0 << 7) | ((1u << n) << 8) | ((uint32_t)n << 16);
-        const float f = (float)rw(s, a);
+        const float f = (float)rw(s, a, p >> 6);
         std::memcpy(&lut[GC_PAIR8_PAIRS + p].y, &f, sizeof(f));
     }
     *unsafe_rows8 = 0;
@@ -180,4 +190,10 @@ void gc_build_pair8_lut(const gc_cell_tables *t, int C, int S, int A, uint2 *lut
         for (int s0 = 0; s0 < S; ++s0)
             for (int x = 0; x < S; ++x)
                 if (se(2, s0, x) == 2) *unsafe_rows8 |= (unsigned long long)(1u << x) << (8 * s0);
+    *unsafe01_rows8 = 0;
+    for (int s0 = 0; s0 < S; ++s0)
+        for (int s1 = 0; s1 < S; ++s1) {
+            const bool uns = C >= 2 ? (se(0, s0, s1) == 2 || se(1, s0, s1) == 2) : (s0 == s1 && se(0, s0, s0) == 2);
+            if (uns) *unsafe01_rows8 |= 1ull << (8 * s0 + s1);
+        }
 }

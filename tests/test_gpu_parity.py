@@ -1147,3 +1147,39 @@ def test_pair8_kernel_vs_oracle(B, O, C, S):
         assert torch.equal(env._count[:n], gen._count[:n]) and torch.equal(env._index[:n], gen._index[:n])
     s = env.stats()
     assert s["env_steps"] == 12 * n == ora.stats[0] and s["unsafe_steps"] == ora.stats[1] and s["count_sum"] == ora.stats[2]
+
+
+
+@pytest.mark.parametrize("episodic", [True, False])
+@pytest.mark.parametrize("C,S", [(1, 5), (2, 8), (3, 6), (4, 8), (5, 5), (10, 8), (9, 7), (13, 5)])
+def test_pair8_kernel_with_noise_vs_oracle(B, O, C, S, episodic):
+    """5..8 levels with Philox noise: the single-cell-table variant of gc_cell_pair8.cu (32-bit draws up to four
+    cells, 16-bit halves with the tie rule beyond) against the oracle and against the generic per-cell kernel, with
+    the fused auto-reset, the final observation, a shard offset and a ragged batch size."""
+    n = 5003
+    difficulty = "hard" if C % 2 else "easy"
+    deadlock = bool(S % 2)
+    off = 987654321096 if C > 4 else 0
+    kw = dict(num_envs=n, n_cells=C, n_states=S, difficulty=difficulty, stochastic=True, deadlock=deadlock, env_seed=C + S,
+              rng_episodic=episodic, max_episode_steps=5, emit_side_effects=False, noise_prob=0.2, env_id_offset=off)
+    env = B.CellularVectorEnv(emit_final_obs=True, **kw)
+    gen = B.CellularVectorEnv(force_generic_kernel=True, **kw)
+    okw = dict(n_envs=n, n_cells=C, n_states=S, difficulty=difficulty, noise=True, deadlock=deadlock, seed=C + S,
+               rng_episodic=episodic, reward="nonlinear_rp", noise_prob=0.2, env_id_offset=off)
+    ora, free = O.OracleEnv(max_episode_steps=5, **okw), O.OracleEnv(**okw)
+    rng = np.random.default_rng(C * 10 + S)
+    for t in range(12):
+        a = rng.integers(0, S, size=(C, n)).astype(np.int8)
+        free.state[:], free.t[:], free.global_step = ora.state, ora.t, ora.global_step
+        env.step_device(dev(a))
+        gen.step_device(dev(a))
+        ora.step(a)
+        free.step(a)
+        assert_matches_oracle(env, ora, check_se=False)
+        assert (host(env._final[:, :n]) == free.state).all()
+        np.testing.assert_allclose(host(env._reward[:n]), host(gen._reward[:n]), rtol=REWARD_RTOL, atol=REWARD_ATOL)
+        assert torch.equal(env.state, gen.state) and torch.equal(env._unsafe[:n], gen._unsafe[:n])
+        assert torch.equal(env._count[:n], gen._count[:n]) and torch.equal(env._index[:n], gen._index[:n])
+    s = env.stats()
+    assert s["env_steps"] == 12 * n == ora.stats[0] and s["unsafe_steps"] == ora.stats[1] and s["count_sum"] == ora.stats[2]
+    assert s["episodes_truncated"] == ora.stats[3]
