@@ -255,7 +255,7 @@ int launch_step(gc_env *env, const StepIO &io, cudaStream_t st)
             e = gc_launch_cell_tma_step(env->tab, io, env->d_pair_lut, env->n_sm, st);
         else if (env->fast_ok)
             e = gc_launch_cell_pair_step(env->tab, io, env->d_pair_lut, mode, env->n_sm, st);
-        else if (env->pair8_ok && mode != GC_RNG_REPLAY && !io.se_row)
+        else if (env->pair8_ok && mode != GC_RNG_REPLAY)
             e = gc_launch_cell_pair8_step(env->tab, io, env->d_pair8_lut, mode, env->n_sm, st);
         else
             e = gc_launch_cell_step(env->tab, io, mode, env->n_sm, st);

@@ -22,7 +22,9 @@
 // Philox word per cell up to GC_NARROW_CELLS cells, 16-bit halves with the exact tie rule beyond (fire_bits_wide).
 // The generic kernel ran these shapes at 0.22 of the HBM roofline (10 cells x 8 levels with noise, 570 us per step
 // of 2^24 envs).
-// Replayed draws, per-cell side-effect rows on request and ragged radices stay with the generic kernel.
+// WITH_SE: row 0 of the side-effects matrix is written as well (entry j from (s'_0, s'_p), p = 1 for j = 0 and
+// p = j otherwise; cells3states3actions3.py:157-212), one byte lookup per (env, cell) in the per-cell tables.
+// Replayed draws and ragged radices stay with the generic kernel.
 #include "gc_device.cuh"
 
 namespace {
@@ -31,7 +33,7 @@ namespace {
 #define GC_PAIR8_MINB 4
 #endif
 
-template <int RNG>
+template <int RNG, bool WITH_SE>
 #ifndef GC_PAIR8_NOISE_MINB
 #define GC_PAIR8_NOISE_MINB 4        // 64 registers (16 bytes spilled): 311 us against 317 us at three blocks, 10 x 8 with noise
 #endif
@@ -42,6 +44,7 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
     constexpr int N_SINGLE = NOISE ? 128 : 64;
     __shared__ uint2 s_pair[NOISE ? 1 : GC_PAIR8_PAIRS];
     __shared__ uint2 s_single[N_SINGLE];
+    __shared__ uint8_t s_se[WITH_SE ? GC_MAX_CELLS : 1][GC_TBL];
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const int C = tab.n_cells;
@@ -53,6 +56,8 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
     if constexpr (!NOISE)
         for (int i = threadIdx.x; i < GC_PAIR8_PAIRS; i += kThreads) s_pair[i] = lut[i];
     if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR8_PAIRS + threadIdx.x];
+    if constexpr (WITH_SE)
+        for (int i = threadIdx.x; i < tab.n_cells * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     pdl_launch_dependents();
     pdl_wait();
@@ -105,6 +110,14 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
             }
         }
 
+        // entry j of row 0 of the side-effects matrix, from (s'_0, s'_p) before an auto-reset
+        [[maybe_unused]] auto emit_se = [&](int j, uint32_t partner_row) {
+            uint32_t sew = 0;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                sew |= static_cast<uint32_t>(s_se[j][((byte_of(s0w, e) & 7u) * GC_LVL_PAD + (byte_of(partner_row, e) & 7u))]) << (8 * e);
+            st_stream_u32(io.se_row + (j * ld + e0), sew);
+        };
         // bookkeeping shared by a pair and a single cell: info low halves, next-state rows of cell c (and d)
         auto account = [&](const uint2 (&ent)[kEPT], int c, bool pair, uint32_t keep_bits) {
 #pragma unroll
@@ -117,6 +130,17 @@ cell_pair8_kernel(const __grid_constant__ CellTables tab, const __grid_constant_
             const uint32_t row_c = prmt(u, v, 0x5410), row_d = prmt(u, v, 0x7632);
             if (c == 0) s0w = row_c;
             if (NOISE && c == 1) s1w = row_c;
+            if constexpr (WITH_SE) {
+                if (c == 0) {
+                    if (pair) { emit_se(0, row_d); emit_se(1, row_d); }
+                    else if (C == 1) emit_se(0, row_c);
+                } else if (c == 1) {                       // single-cell lookups only (pairs start at even cells)
+                    emit_se(0, row_c); emit_se(1, row_c);
+                } else {
+                    emit_se(c, row_c);
+                    if (pair) emit_se(c + 1, row_d);
+                }
+            }
             const uint32_t out_c = (row_c & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c])) & ~keep);
             st_stream_u32(io.state + (c * ld + e0), out_c);
             if (io.final_state) st_stream_u32(io.final_state + (c * ld + e0), row_c);
@@ -229,9 +253,13 @@ cudaError_t gc_launch_cell_pair8_step(const CellTables &tab, const StepIO &io, c
                                       cudaStream_t st)
 {
     const int64_t n = io.end - io.begin;
-    if (rng_mode == GC_RNG_PHILOX)
-        return launch_step_kernel(cell_pair8_kernel<GC_RNG_PHILOX>, grid_for<cell_pair8_kernel<GC_RNG_PHILOX>>(n, n_sm), kThreads, 0,
-                                  st, tab, io, lut);
-    return launch_step_kernel(cell_pair8_kernel<GC_RNG_NONE>, grid_for<cell_pair8_kernel<GC_RNG_NONE>>(n, n_sm), kThreads, 0, st,
-                              tab, io, lut);
+#define GC_PAIR8_LAUNCH(RNG, SE) \
+    return launch_step_kernel(cell_pair8_kernel<RNG, SE>, grid_for<cell_pair8_kernel<RNG, SE>>(n, n_sm), kThreads, 0, st, tab, io, lut)
+    if (rng_mode == GC_RNG_PHILOX) {
+        if (io.se_row) GC_PAIR8_LAUNCH(GC_RNG_PHILOX, true);
+        GC_PAIR8_LAUNCH(GC_RNG_PHILOX, false);
+    }
+    if (io.se_row) GC_PAIR8_LAUNCH(GC_RNG_NONE, true);
+    GC_PAIR8_LAUNCH(GC_RNG_NONE, false);
+#undef GC_PAIR8_LAUNCH
 }

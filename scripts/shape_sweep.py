@@ -11,7 +11,8 @@ import gym_cellular_b200 as B   # noqa: E402
 CASES = [dict(n_cells=3, n_states=3), dict(n_cells=3, n_states=3, stochastic=True), dict(n_cells=2, n_states=3),
          dict(n_cells=8, n_states=4), dict(n_cells=8, n_states=4, stochastic=True), dict(n_cells=16, n_states=4),
          dict(n_cells=16, n_states=4, stochastic=True), dict(n_cells=16, n_states=4, emit_side_effects=True),
-         dict(n_cells=10, n_states=8), dict(n_cells=10, n_states=8, stochastic=True), dict(n_cells=6, n_states=5), dict(kind="gridworld"), dict(kind="gridworld", max_episode_steps=128)]
+         dict(n_cells=10, n_states=8), dict(n_cells=10, n_states=8, stochastic=True), dict(n_cells=6, n_states=5), dict(kind="gridworld"), dict(kind="gridworld", max_episode_steps=128),
+         dict(n_cells=10, n_states=8, emit_side_effects=True), dict(n_cells=10, n_states=8, stochastic=True, emit_side_effects=True)]
 if "--cells" in sys.argv:      # every cell count of the pair-table kernels, deterministic and stochastic
     CASES = [dict(n_cells=c, n_states=4, stochastic=st) for st in (False, True) for c in range(1, 17)]
 if "--only" in sys.argv:       # one case by position (for an ncu capture of its kernel)

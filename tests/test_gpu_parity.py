@@ -1121,7 +1121,8 @@ def test_host_path_at_bench_size(B, layout):
 @pytest.mark.parametrize("C,S", [(1, 5), (2, 8), (3, 6), (5, 5), (10, 8), (9, 7), (13, 5), (4, 8)])
 def test_pair8_kernel_vs_oracle(B, O, C, S):
     """5..8 levels, deterministic: the 3-bit pair-table kernel (gc_cell_pair8.cu) against the oracle, with the
-    fused auto-reset, the final observation and ragged batch sizes; and against the generic per-cell kernel."""
+    fused auto-reset, the final observation and ragged batch sizes; and against the generic per-cell kernel.
+    A third handle also writes the side-effect rows (the WITH_SE instantiation)."""
     n = 5003
     difficulty = "hard" if C % 2 else "easy"
     reward = "multiple_optima" if S % 2 else "right_polarizing"
@@ -1129,6 +1130,7 @@ def test_pair8_kernel_vs_oracle(B, O, C, S):
               max_episode_steps=5, emit_side_effects=False)
     env = B.CellularVectorEnv(emit_final_obs=True, **kw)
     gen = B.CellularVectorEnv(force_generic_kernel=True, **kw)
+    wse = B.CellularVectorEnv(**dict(kw, emit_side_effects=True))
     ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, difficulty=difficulty, reward=reward, max_episode_steps=5)
     free = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, difficulty=difficulty, reward=reward)
     rng = np.random.default_rng(C * 10 + S)
@@ -1137,9 +1139,11 @@ def test_pair8_kernel_vs_oracle(B, O, C, S):
         free.state[:], free.t[:] = ora.state, ora.t
         env.step_device(dev(a))
         gen.step_device(dev(a))
+        wse.step_device(dev(a))
         ora.step(a)
         free.step(a)
         assert_matches_oracle(env, ora, check_se=False)
+        assert_matches_oracle(wse, ora, check_se=True)
         assert (host(env._final[:, :n]) == free.state).all()
         # (pair sums are rounded once per pair, the generic kernel adds cell by cell: rewards agree to rounding)
         np.testing.assert_allclose(host(env._reward[:n]), host(gen._reward[:n]), rtol=REWARD_RTOL, atol=REWARD_ATOL)
@@ -1164,6 +1168,7 @@ def test_pair8_kernel_with_noise_vs_oracle(B, O, C, S, episodic):
               rng_episodic=episodic, max_episode_steps=5, emit_side_effects=False, noise_prob=0.2, env_id_offset=off)
     env = B.CellularVectorEnv(emit_final_obs=True, **kw)
     gen = B.CellularVectorEnv(force_generic_kernel=True, **kw)
+    wse = B.CellularVectorEnv(**dict(kw, emit_side_effects=True))
     okw = dict(n_envs=n, n_cells=C, n_states=S, difficulty=difficulty, noise=True, deadlock=deadlock, seed=C + S,
                rng_episodic=episodic, reward="nonlinear_rp", noise_prob=0.2, env_id_offset=off)
     ora, free = O.OracleEnv(max_episode_steps=5, **okw), O.OracleEnv(**okw)
@@ -1173,9 +1178,11 @@ def test_pair8_kernel_with_noise_vs_oracle(B, O, C, S, episodic):
         free.state[:], free.t[:], free.global_step = ora.state, ora.t, ora.global_step
         env.step_device(dev(a))
         gen.step_device(dev(a))
+        wse.step_device(dev(a))
         ora.step(a)
         free.step(a)
         assert_matches_oracle(env, ora, check_se=False)
+        assert_matches_oracle(wse, ora, check_se=True)
         assert (host(env._final[:, :n]) == free.state).all()
         np.testing.assert_allclose(host(env._reward[:n]), host(gen._reward[:n]), rtol=REWARD_RTOL, atol=REWARD_ATOL)
         assert torch.equal(env.state, gen.state) and torch.equal(env._unsafe[:n], gen._unsafe[:n])
