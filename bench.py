@@ -638,6 +638,21 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
     # the per-iteration all-reduce of the statistics belongs to the multi-GPU path; one rank has nothing to reduce
     in_loop = reducer if dist is not None else None
     ms, launches, clocks, host_us = time_device_path(batches, steps, warmup, dist, device, device.index, in_loop)
+    # Small shards: gc_step_many runs the bound steps of a call inside ONE kernel (state in registers between the steps,
+    # every per-step output written at every step; include/gym_cellular_b200.h).  The same loop is then timed with one
+    # launch per step as well (GC_B200_STEP_MANY_FUSED=0, read by the library at every call) and reported beside it.
+    sep_res, sep_steps = None, 0
+    if launches < steps * len(batches):
+        os.environ["GC_B200_STEP_MANY_FUSED"] = "0"
+        try:
+            s_ms, s_launches, _, s_host_us = time_device_path(batches, steps, warmup, dist, device, device.index, in_loop)
+        finally:
+            os.environ.pop("GC_B200_STEP_MANY_FUSED", None)
+        sep_steps = steps + warmup
+        sep_res = {"value": world * n_rank * steps / (s_ms * 1e-3), "ms_per_step": s_ms / steps, "gpu_launches": s_launches * world,
+                   "host_us_per_launch": round(s_host_us, 2),
+                   "roofline_frac": roofline_of(workload, batches, s_ms * 1e-3 / steps)["frac"],
+                   "note": "one kernel launch per step (programmatic dependent launch, cached graph replay)"}
     single = dist is None and side
     graph_res = None
     if WORKLOADS[workload]["l2_resident"] and single:
@@ -673,7 +688,7 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
                   "note": "fused rollout: state in registers, actions generated in-kernel (not per-step step())"}
     # episode statistics over all ranks: the path's only collective; totals must add up exactly
     totals = reducer.start(sum_stats(batches)).result()
-    expect = world * n_rank * (steps + warmup + (g_steps + RING if graph_res else 0) + (K * (reps + 1) if ro_res else 0))
+    expect = world * n_rank * (steps + warmup + sep_steps + (g_steps + RING if graph_res else 0) + (K * (reps + 1) if ro_res else 0))
     stats_ok = totals["env_steps"] == expect
     step_s = ms * 1e-3 / steps
     res = {
@@ -687,7 +702,19 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
         "episode_stats": dict(totals, env_steps_expected=expect, consistent=stats_ok),
         "cuda_graph": graph_res,
         "fused_rollout": ro_res,
+        "steps_per_launch": round(steps * len(batches) / max(launches, 1), 1),
+        "separate_launches": sep_res,
     }
+    if sep_res is not None:
+        # the dominant kernel is the many-step kernel: its launch moves the algorithmic bytes of all its steps
+        spl = steps * len(batches) / max(launches, 1)
+        res["roofline"]["algorithmic_bytes_per_step"] = res["roofline"]["algorithmic_bytes_per_launch"]
+        res["roofline"]["algorithmic_bytes_per_launch"] = int(res["roofline"]["algorithmic_bytes_per_launch"] * spl)
+        res["roofline"]["kernels_per_step"] = round(len(batches) / spl, 4)
+        res["step_many"] = ("bound steps of one gc_step_many call run inside ONE kernel (shards <= 2^21 envs): state and episode "
+                            "step in registers between the steps, actions read and every per-step output written at every step; "
+                            "bit-identical to separate launches (tests/test_gpu_many.py); `separate_launches` = the same loop with "
+                            "one launch per step")
     for b in batches:
         b["env"].close()
     del batches
@@ -823,6 +850,8 @@ def main():
                             "l2_resident": r["roofline"]["l2_resident"], "e2e": r["e2e"]["value"],
                             "e2e_bytes_per_step": [r["e2e"]["h2d_bytes_per_step"], r["e2e"]["d2h_bytes_per_step"]],
                             "kernels_per_step": r["roofline"]["kernels_per_step"], "cuda_graph": r["cuda_graph"],
+                            "steps_per_launch": r["steps_per_launch"], "separate_launches": r["separate_launches"],
+                            "step_many": r.get("step_many"),
                             "fused_rollout": r["fused_rollout"], "episode_stats_consistent": r["episode_stats"]["consistent"],
                             "packed": None if "packed" not in r else
                             {k: r["packed"][k] for k in ("value", "ms_per_step")} | {"roofline_frac": r["packed"]["roofline"]["frac"],
@@ -854,7 +883,10 @@ def main():
             "roofline": main_res["roofline"], "packed": main_res.get("packed"),
             "episode_stats": main_res["episode_stats"],
             "fused_rollout": main_res["fused_rollout"], "cuda_graph": main_res["cuda_graph"],
+            "steps_per_launch": main_res["steps_per_launch"],
         }
+        if main_res["separate_launches"] is not None:
+            line["separate_launches"], line["step_many"] = main_res["separate_launches"], main_res["step_many"]
         if check is not None:
             line["shard_check"] = check["result"]
             line["shard_check_detail"] = check

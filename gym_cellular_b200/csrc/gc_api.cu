@@ -658,6 +658,50 @@ bool many_graphs_enabled(const gc_env *env)
     static const bool on = [] { const char *v = std::getenv("GC_B200_STEP_MANY_GRAPH"); return !(v && v[0] == '0'); }();
     return on && env->cfg.n_envs <= kManyGraphMaxEnvs;
 }
+
+// Small shards whose bound slots differ ONLY in their action buffers (the usual ring of action buffers around one
+// set of in-place state / output tensors) run all their steps in one launch: state in registers between the steps,
+// every per-step output written as the separate launches write it (gc_cell_fast.cu: cell_pair_many_kernel).
+// GC_B200_STEP_MANY_FUSED=0 switches it off (the cached graph of chained launches is used instead).
+bool many_fusable(const gc_env *env, const int32_t *slots, int32_t n_slots)
+{
+    const char *v = std::getenv("GC_B200_STEP_MANY_FUSED");          // read at every call: benches measure both ways
+    if ((v && v[0] == '0') || env->cfg.n_envs > kManyGraphMaxEnvs || env->final_state) return false;
+    if (env->cfg.kind == GC_KIND_CELLULAR) {
+        if (!env->fast_ok || env->cfg.n_cells > GC_MANY_MAX_CELLS) return false;
+    }
+    for (int32_t i = 0; i < n_slots; ++i)
+        if (env->bound_set[slots[i]] != 1) return false;
+    const StepIO &a = env->bound[slots[0]];
+    for (int32_t i = 1; i < n_slots; ++i) {
+        const StepIO &b = env->bound[slots[i]];
+        if (a.state != b.state || a.t != b.t || a.reward != b.reward || a.index != b.index || a.terminated != b.terminated ||
+            a.truncated != b.truncated || a.unsafe != b.unsafe || a.count != b.count || a.se_row != b.se_row ||
+            a.stats != b.stats || a.final_state != b.final_state)
+            return false;
+    }
+    return a.final_state == nullptr && a.replay == nullptr;
+}
+
+constexpr int32_t kManyFusedMaxSteps = 4096;       // steps per launch
+
+int launch_many_fused(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t first, int32_t n_steps, cudaStream_t st)
+{
+    ManyIO mio;
+    mio.io = env->bound[slots[0]];
+    for (int32_t i = 0; i < n_slots; ++i) mio.tape[i] = env->bound[slots[(first + i) % n_slots]].actions;
+    for (int32_t i = n_slots; i < GC_MAX_BINDINGS; ++i) mio.tape[i] = nullptr;
+    mio.n_tape = n_slots;
+    mio.n_steps = n_steps;
+    const bool draws = (env->cfg.flags & GC_F_NOISE) && env->tab.noise_thr_nz;
+    const cudaError_t e = env->cfg.kind == GC_KIND_CELLULAR
+        ? gc_launch_cell_pair_many(env->tab, mio, env->d_pair_lut, draws ? GC_RNG_PHILOX : GC_RNG_NONE, env->n_sm, st)
+        : gc_launch_grid_many(env->grid, mio, env->n_sm, st);
+    if (e != cudaSuccess) return fail(GC_ERR_CUDA, "many-step kernel launch failed: %s", cudaGetErrorString(e));
+    env->launches += 1;
+    env->global_step += n_steps;
+    return GC_OK;
+}
 }  // namespace
 
 int gc_prepare_step_many(gc_env *env, const int32_t *slots, int32_t n_slots)
@@ -680,6 +724,18 @@ int gc_step_many(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t n_s
     GC_ON_DEVICE(env->cfg.device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int32_t done = 0;
+    for (int32_t i = 0; i < n_slots; ++i)
+        if (slots[i] < 0 || slots[i] >= GC_MAX_BINDINGS || !env->bound_set[slots[i]])
+            return fail(GC_ERR_INVALID, "no binding in slot %d", slots[i]);
+    // Small shards with one set of in-place buffers: all steps in one launch (many_fusable)
+    if (n_steps >= 2 && n_slots <= GC_MAX_BINDINGS && many_fusable(env, slots, n_slots)) {
+        for (; done < n_steps;) {
+            const int32_t k = n_steps - done < kManyFusedMaxSteps ? n_steps - done : kManyFusedMaxSteps;
+            if (int rc = launch_many_fused(env, slots, n_slots, done % n_slots, k, st)) return rc;
+            done += k;
+        }
+        return GC_OK;
+    }
     // Launch-bound batch sizes: whole passes over the slot list are replayed from a cached CUDA graph (one host
     // call per n_slots kernels instead of one per kernel; the RNG step counter lives in device memory, so every
     // replay draws fresh numbers).  Not while the caller's stream is itself being captured.

@@ -77,7 +77,8 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
                                          const uint2 *s_single, const uint8_t (*s_se)[GC_TBL], int c0,
                                          uint32_t e0, int rem, uint32_t gid_lo, uint32_t gid_hi, uint32_t step_counter,
                                          const int (&tin)[kEPT], uint32_t keep, const uint32_t (&sw)[4],
-                                         const uint32_t (&aw)[4], const uint32_t (&fire16)[kEPT], EnvAcc &acc)
+                                         const uint32_t (&aw)[4], const uint32_t (&fire16)[kEPT], EnvAcc &acc,
+                                         uint32_t (&next)[4])
 {
     // fb[e]: bit i = the noise draw of cell (c0 + i) of env e fired (the table ignores the bit where the
     // (level, action) pair consumes no draw).  The four random words are reduced to four bits at once so
@@ -159,6 +160,7 @@ __device__ __forceinline__ void do_cells(const CellTables &tab, const StepIO &io
             st_stream_u32(io.se_row + ((c0 + i) * ld + e0), sew);
         }
         const uint32_t out = (rows[i] & keep) | ((0x01010101u * static_cast<uint8_t>(tab.init[c0 + i])) & ~keep);
+        next[i] = out;                    // (used by the many-step kernel only: the state stays in registers there)
         st_stream_u32(io.state + ((c0 + i) * ld + e0), out);
         if (io.final_state) st_stream_u32(io.final_state + ((c0 + i) * ld + e0), rows[i]);
         q += out * tab.place4[i];
@@ -281,21 +283,22 @@ cell_pair_kernel(const __grid_constant__ CellTables tab, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.idx[e] = 0; }
         acc.sum01 = acc.sum23 = acc.or01 = acc.or23 = acc.s0w = acc.s1w = 0;
+        uint32_t nx[4];                   // next rows of a group: not needed here (every step reloads its state)
 
         if (NG == 0) {
-            do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc);
+            do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc, nx);
         } else {
-            do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc);
+            do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc, nx);
 #pragma unroll 1
             for (int g = 1; g < NG; ++g) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { sa[i] = sb[i]; aa[i] = ab[i]; }
                 if (g + 1 < NG) load_cells<4>(io, 4 * (g + 1), e0, sb, ab);
                 else if (R > 0) load_cells<R>(io, 4 * NG, e0, sb, ab);
-                do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc);
+                do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sa, aa, fire16, acc, nx);
             }
             if (R > 0)
-                do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sb, ab, fire16, acc);
+                do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sb, ab, fire16, acc, nx);
         }
 
         // unsafe / count for the four envs at once (byte lanes): the count and the presence / flag bytes
@@ -345,6 +348,151 @@ cudaError_t launch_pair_cr(const CellTables &tab, const StepIO &io, const uint2 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// gc_step_many in ONE launch (small shards, gc_api.cu: many_fusable): the n_steps bound steps of a handle whose
+// slots differ only in their action buffers.  A step of a 65,536-env shard is a 3 us launch around 0.3 us of work
+// (BASELINE config 2), so the steps are run back to back by the thread that owns the envs: state and episode step
+// stay in registers between two steps, the actions of step k + 1 are requested before step k is computed, and
+// EVERY per-step output (state, t, reward, index, flags, side-effect row, statistics) is written at every step
+// exactly as the n_steps separate launches write it -- same do_cells, same epilogue, same Philox counters
+// (global step of the launch + k) -- so the results are bit-identical to them (tests/test_gpu_many.py).
+template <int C, int RNG, bool WITH_SE>
+__global__ void __launch_bounds__(kThreads, 2)
+cell_pair_many_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ ManyIO mio, const uint2 *__restrict__ lut)
+{
+    const StepIO &io = mio.io;
+    constexpr int NG = C / 4, R = C % 4, G = (C + 3) / 4;
+    constexpr int N_PAIR = (RNG == GC_RNG_NONE) ? 256 : GC_PAIR_LUT_PAIRS;
+    constexpr int N_SINGLE = (RNG == GC_RNG_NONE) ? 16 : 32;
+    __shared__ uint2 s_pair[N_PAIR];
+    __shared__ uint2 s_single[N_SINGLE];
+    __shared__ uint8_t s_se[WITH_SE ? C : 1][GC_TBL];
+    __shared__ unsigned long long s_stats[5];
+    __shared__ StepCounterShared s_ctr;
+
+    for (int i = threadIdx.x; i < N_PAIR; i += kThreads) s_pair[i] = lut[i];
+    if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
+    if (WITH_SE)
+        for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
+    pdl_launch_dependents();
+    pdl_wait();
+    step_counter_read(io, &s_ctr);
+    __syncthreads();
+    const uint32_t step0 = step_counter_arrive(io, &s_ctr);
+
+    const uint32_t ld = static_cast<uint32_t>(io.ld);
+    const uint32_t stride = gridDim.x * kThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
+    uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
+    long long st_reward = 0;
+#pragma unroll 1
+    for (uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kThreads + threadIdx.x) * kEPT; e0 < e_end; e0 += stride) {
+        const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
+        const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
+        uint32_t sw[G][4], an[G][4];                       // state rows; action rows of the NEXT step
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            sw[c / 4][c % 4] = ld_stream_u32(io.state + (c * ld + e0));
+            an[c / 4][c % 4] = ld_stream_u32(mio.tape[0] + (c * ld + e0));
+        }
+        const int4 t4 = ld_stream_v4(io.t + e0);
+        int t[kEPT] = {t4.x, t4.y, t4.z, t4.w};
+        int slot = 0;
+#pragma unroll 1
+        for (int k = 0; k < mio.n_steps; ++k) {
+            uint32_t aa[G][4];
+#pragma unroll
+            for (int c = 0; c < C; ++c) aa[c / 4][c % 4] = an[c / 4][c % 4];
+            slot = slot + 1 == mio.n_tape ? 0 : slot + 1;
+            if (k + 1 < mio.n_steps) {
+                const int8_t *const nxt = mio.tape[slot];
+#pragma unroll
+                for (int c = 0; c < C; ++c) an[c / 4][c % 4] = ld_stream_u32(nxt + (c * ld + e0));
+            }
+            const int tin[kEPT] = {t[0], t[1], t[2], t[3]};
+            int tn[kEPT] = {t[0] + 1, t[1] + 1, t[2] + 1, t[3] + 1};
+            uint32_t trunc_w = 0, keep = 0xFFFFFFFFu;
+            if (io.max_episode_steps > 0) {
+#pragma unroll
+                for (int e = 0; e < kEPT; ++e)
+                    if (tn[e] >= io.max_episode_steps) { tn[e] = 0; trunc_w |= 1u << (8 * e); keep &= ~(0xFFu << (8 * e)); }
+            }
+            const uint32_t step_counter = (RNG == GC_RNG_PHILOX) ? step0 + static_cast<uint32_t>(k) : 0u;
+            uint32_t fire16[kEPT] = {0, 0, 0, 0};
+            if (RNG == GC_RNG_PHILOX && C > GC_NARROW_CELLS) {
+#pragma unroll
+                for (int e = 0; e < kEPT; ++e)
+                    fire16[e] = fire_bits_wide<(C + 7) / 8>(tab, gid_lo | e, gid_hi, io.episodic ? static_cast<uint32_t>(tin[e]) : step_counter,
+                                                            io.round_key);
+            }
+            EnvAcc acc;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) { acc.r[e] = 0.f; acc.idx[e] = 0; }
+            acc.sum01 = acc.sum23 = acc.or01 = acc.or23 = acc.s0w = acc.s1w = 0;
+            uint32_t nx[G][4];
+            if constexpr (NG == 0) {
+                do_cells<R, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sw[0], aa[0], fire16, acc, nx[0]);
+            } else {
+                do_cells<4, C, RNG, WITH_SE, true>(tab, io, s_pair, s_single, s_se, 0, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sw[0], aa[0], fire16, acc, nx[0]);
+#pragma unroll
+                for (int g = 1; g < NG; ++g)
+                    do_cells<4, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * g, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sw[g], aa[g], fire16, acc, nx[g]);
+                if constexpr (R > 0)
+                    do_cells<R, C, RNG, WITH_SE, false>(tab, io, s_pair, s_single, s_se, 4 * NG, e0, rem, gid_lo, gid_hi, step_counter, tin, keep, sw[NG], aa[NG], fire16, acc, nx[NG]);
+            }
+            // (the epilogue of cell_pair_kernel, word for word)
+            float rout[kEPT];
+            log2_1p_x4(tab.reward_log2, acc.r, rout);
+            const uint32_t count_w = prmt(acc.sum01, acc.sum23, 0x6420) & 0x1F1F1F1Fu;
+            const uint32_t present = prmt(acc.or01, acc.or23, 0x7531);
+            const uint32_t nib = acc.s0w | (acc.s0w >> 4);
+            const uint32_t rowmask = prmt(tab.unsafe_rows, 0u, prmt(nib, 0u, 0x4420) & 0x3333u);
+            const uint32_t unsafe_w = ((((present & rowmask) + 0x0F0F0F0Fu) | present) >> 4) & 0x01010101u;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e)
+                if (e < rem) st_reward += __float2int_rn(rout[e] * 16777216.0f);
+            {
+                const uint32_t vb = valid_bytes(rem);
+                st_steps += rem;
+                st_unsafe = add_bytes(unsafe_w & vb, st_unsafe);
+                st_count = add_bytes(count_w & vb, st_count);
+                st_trunc = add_bytes(trunc_w & vb, st_trunc);
+            }
+            st_stream_v4(io.t + e0, make_int4(tn[0], tn[1], tn[2], tn[3]));
+            st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
+                                                   __float_as_int(rout[2]), __float_as_int(rout[3])));
+            st_stream_v4(io.index + e0, make_int4(acc.idx[0], acc.idx[1], acc.idx[2], acc.idx[3]));
+            st_stream_u32(io.terminated + e0, 0u);
+            st_stream_u32(io.truncated + e0, trunc_w);
+            st_stream_u32(io.unsafe + e0, unsafe_w);
+            st_stream_u32(io.count + e0, count_w);
+#pragma unroll
+            for (int c = 0; c < C; ++c) sw[c / 4][c % 4] = nx[c / 4][c % 4];
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) t[e] = tn[e];
+        }
+    }
+    if (io.stats) {
+        const ThreadStats ts = {st_steps, st_unsafe, st_count, st_trunc, st_reward};
+        block_flush_stats(ts, s_stats, io.stats);
+    }
+    // the block that arrived last advances the device step counter by the steps of this launch
+    if (threadIdx.x == 0 && io.done_ctr != nullptr && s_ctr.arrived == gridDim.x - 1) {
+        *io.done_ctr = 0u;
+        *const_cast<uint32_t *>(io.step_ctr) = s_ctr.step + static_cast<uint32_t>(mio.n_steps);
+    }
+}
+
+template <int C, int RNG>
+cudaError_t launch_pair_many_cr(const CellTables &tab, const ManyIO &mio, const uint2 *lut, int n_sm, cudaStream_t st)
+{
+    const int64_t n = mio.io.end - mio.io.begin;
+    if (mio.io.se_row)
+        return launch_step_kernel(cell_pair_many_kernel<C, RNG, true>, grid_for<cell_pair_many_kernel<C, RNG, true>>(n, n_sm), kThreads, 0, st, tab, mio, lut);
+    return launch_step_kernel(cell_pair_many_kernel<C, RNG, false>, grid_for<cell_pair_many_kernel<C, RNG, false>>(n, n_sm), kThreads, 0, st, tab, mio, lut);
+}
+
 template <int C>
 cudaError_t launch_pair_c(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode, int n_sm,
                           cudaStream_t st)
@@ -365,6 +513,20 @@ cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, co
 #define GC_CASE(C) case C: return launch_pair_c<C>(tab, io, lut, rng_mode, n_sm, st);
         GC_CASE(1) GC_CASE(2) GC_CASE(3) GC_CASE(4) GC_CASE(5) GC_CASE(6) GC_CASE(7) GC_CASE(8)
         GC_CASE(9) GC_CASE(10) GC_CASE(11) GC_CASE(12) GC_CASE(13) GC_CASE(14) GC_CASE(15) GC_CASE(16)
+#undef GC_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// gc_step_many in one launch: up to GC_MANY_MAX_CELLS cells (wider envs at these batch sizes are not launch-bound)
+cudaError_t gc_launch_cell_pair_many(const CellTables &tab, const ManyIO &mio, const uint2 *lut, int rng_mode, int n_sm,
+                                     cudaStream_t st)
+{
+    if (rng_mode != GC_RNG_NONE && rng_mode != GC_RNG_PHILOX) return cudaErrorInvalidValue;
+    switch (tab.n_cells) {
+#define GC_CASE(C) case C: return rng_mode == GC_RNG_PHILOX ? launch_pair_many_cr<C, GC_RNG_PHILOX>(tab, mio, lut, n_sm, st) \
+                                                            : launch_pair_many_cr<C, GC_RNG_NONE>(tab, mio, lut, n_sm, st);
+        GC_CASE(1) GC_CASE(2) GC_CASE(3) GC_CASE(4) GC_CASE(5) GC_CASE(6) GC_CASE(7) GC_CASE(8)
 #undef GC_CASE
     default: return cudaErrorInvalidValue;
     }

@@ -255,6 +255,151 @@ grid_step_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ 
     step_counter_finish(io, &s_ctr);
 }
 
+// ---------------------------------------------------------------------------------------------
+// gc_step_many in ONE launch for small grid-world shards (gc_api.cu: many_fusable; see cell_pair_many_kernel in
+// gc_cell_fast.cu): the thread that owns four envs runs their n_steps bound steps back to back -- codes and
+// episode steps in registers, the actions of step k + 1 requested before step k is computed, the table staged
+// once -- and writes every per-step output at every step as the separate launches do.  The step itself is the
+// Philox path of grid_step_kernel word for word (same table index masks, same dispersal patch, same counters:
+// global step of the launch + k), so the results are bit-identical to n_steps launches (tests/test_gpu_many.py).
+__global__ void __launch_bounds__(kGridThreads, GC_GRID_MINB)
+grid_many_kernel(const __grid_constant__ GridParams gp, const __grid_constant__ ManyIO mio)
+{
+    const StepIO &io = mio.io;
+    extern __shared__ __align__(16) uint32_t s_lut[];          // kGridLutAlloc entries (the padding included)
+    __shared__ unsigned long long s_stats[5];
+    __shared__ StepCounterShared s_ctr;
+    const uint32_t ld = static_cast<uint32_t>(io.ld);
+    const uint32_t e_end = static_cast<uint32_t>(io.end), stride = gridDim.x * kGridThreads * kEPT;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gp.lut);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (int i = threadIdx.x; i < kGridLutAlloc / 4; i += kGridThreads) dst[i] = src[i];
+    }
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
+    pdl_launch_dependents();
+    pdl_wait();
+    step_counter_read(io, &s_ctr);
+    __syncthreads();
+    const uint32_t step0 = step_counter_arrive(io, &s_ctr);
+    uint32_t st_count = 0, st_trunc = 0, st_reward = 0, bad_bits = 0;
+#pragma unroll 1
+    for (uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kGridThreads + threadIdx.x) * kEPT; e0 < e_end; e0 += stride) {
+        const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
+        const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
+        const uint64_t grp = gid0 >> 2;
+        uint32_t s0w = ld_stream_u32(io.state + e0), s1w = ld_stream_u32(io.state + (ld + e0));
+        uint32_t n_a0 = ld_stream_u32(mio.tape[0] + e0), n_a1 = ld_stream_u32(mio.tape[0] + (ld + e0));
+        const int4 t4 = ld_stream_v4(io.t + e0);
+        int tin[kEPT] = {t4.x, t4.y, t4.z, t4.w};
+        int slot = 0;
+#pragma unroll 1
+        for (int k = 0; k < mio.n_steps; ++k) {
+            const uint32_t a0w = n_a0, a1w = n_a1;
+            slot = slot + 1 == mio.n_tape ? 0 : slot + 1;
+            if (k + 1 < mio.n_steps) {
+                const int8_t *const nxt = mio.tape[slot];
+                n_a0 = ld_stream_u32(nxt + e0); n_a1 = ld_stream_u32(nxt + (ld + e0));
+            }
+            const uint32_t step_counter = step0 + static_cast<uint32_t>(k);
+            const uint32_t s0m = s0w & 0x1F1F1F1Fu, s1m = s1w & 0x1F1F1F1Fu;
+            const uint32_t actw = (a0w & 0x07070707u) + (a1w & 0x07070707u) * 5u;
+            const uint32_t i02 = ((s0m & 0x00FF00FFu) + 20u * (s1m & 0x00FF00FFu)) * 25u + (actw & 0x00FF00FFu);
+            const uint32_t i13 = (((s0m >> 8) & 0x00FF00FFu) + 20u * ((s1m >> 8) & 0x00FF00FFu)) * 25u + ((actw >> 8) & 0x00FF00FFu);
+            uint32_t ent[kEPT];
+            ent[0] = s_lut[i02 & 0xFFFFu]; ent[1] = s_lut[i13 & 0xFFFFu];
+            ent[2] = s_lut[i02 >> 16]; ent[3] = s_lut[i13 >> 16];
+            uint32_t trig[kEPT];
+            const bool same_t = !io.episodic || (tin[0] == tin[1] && tin[1] == tin[2] && tin[2] == tin[3]);
+            if (same_t) {
+                const uint32_t ctr = io.episodic ? static_cast<uint32_t>(tin[0]) : step_counter;
+                philox4x32_10(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32), ctr, 0u, io.round_key, trig);
+            } else {
+#pragma unroll 1
+                for (int e = 0; e < kEPT; ++e) {
+                    uint32_t w[4];
+                    philox4x32_10(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32),
+                                  static_cast<uint32_t>(tin[e]), 0u, io.round_key, w);
+                    trig[e] = w[e];
+                }
+            }
+            const uint32_t thr = gp.dispersal_thr_m1;
+            if (gp.dispersal_thr_nz && (trig[0] <= thr || trig[1] <= thr || trig[2] <= thr || trig[3] <= thr)) {
+#pragma unroll
+                for (int e = 0; e < kEPT; ++e) {
+                    uint32_t x = ent[e];
+                    const uint32_t w = trig[e];
+                    if (w <= thr && ((x >> 18) & 3u) < 2u) {
+                        const uint32_t Nk = ((w >> 1) & 1u) | ((w & 1u) << 1);
+                        const uint32_t sh = (w & 4u) << 1;                               // 8 k
+                        x = (x & ~(3u << sh)) | (Nk << sh);
+                        const uint32_t Tp = (byte_of(s0w, e) & 3u) | ((byte_of(s1w, e) & 3u) << 8);
+                        const uint32_t Np = x & 0x0303u;
+                        const uint32_t rew = __popc(Tp & ~Np);
+                        const uint32_t se1 = (Np & 3u) ? 1u : 0u, se0 = (se1 && (Np & 0x0300u)) ? 1u : 0u;
+                        ent[e] = (x & ~((3u << 16) | (3u << 20))) | (rew << 16) | (se0 << 20) | (se1 << 21);
+                    }
+                }
+            }
+            const uint32_t m01 = prmt(ent[0], ent[1], 0x0062), m23 = prmt(ent[2], ent[3], 0x0062);
+            const uint32_t miscw = prmt(m01, m23, 0x5410);
+            const uint32_t vbytes = valid_bytes(rem);
+            bad_bits |= miscw & vbytes;
+            const uint32_t rew_w = miscw & 0x03030303u, count_w = (miscw >> 2) & 0x03030303u;
+            const uint32_t se0w = (miscw >> 4) & 0x01010101u, se1w = (miscw >> 5) & 0x01010101u;
+            const uint32_t u = prmt(ent[0], ent[1], 0x5140), v = prmt(ent[2], ent[3], 0x5140);
+            uint32_t row0 = prmt(u, v, 0x5410), row1 = prmt(u, v, 0x7632);
+            uint32_t trunc_w = 0;
+            int tout[kEPT] = {tin[0] + 1, tin[1] + 1, tin[2] + 1, tin[3] + 1};
+            if (io.max_episode_steps > 0) {
+#pragma unroll
+                for (int e = 0; e < kEPT; ++e) {
+                    const bool tr = tout[e] >= io.max_episode_steps;
+                    tout[e] = tr ? 0 : tout[e];
+                    trunc_w |= (tr ? 1u : 0u) << (8 * e);
+                }
+                const uint32_t gone = trunc_w * 0xFFu;
+                row0 = (row0 & ~gone) | (0x0F0F0F0Fu & gone);                       // reset codes 15 / 18: grid_world.py:238-259
+                row1 = (row1 & ~gone) | (0x12121212u & gone);
+            }
+            float rout[kEPT];
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) rout[e] = __uint_as_float(prmt(rew_w, 0x4B000000u, 0x7540u + e)) - 8388608.0f;
+            const uint32_t x02 = (row0 & 0x00FF00FFu) + 20u * (row1 & 0x00FF00FFu);
+            const uint32_t x13 = ((row0 >> 8) & 0x00FF00FFu) + 20u * ((row1 >> 8) & 0x00FF00FFu);
+            st_count = add_bytes(count_w & vbytes, st_count);
+            st_trunc = add_bytes(trunc_w & vbytes, st_trunc);
+            st_reward = add_bytes(rew_w & vbytes, st_reward);
+            st_stream_u32(io.state + e0, row0);
+            st_stream_u32(io.state + (ld + e0), row1);
+            if (io.se_row) {
+                st_stream_u32(io.se_row + e0, se0w);
+                st_stream_u32(io.se_row + (ld + e0), se1w);
+            }
+            st_stream_v4(io.t + e0, make_int4(tout[0], tout[1], tout[2], tout[3]));
+            st_stream_v4(io.reward + e0, make_int4(__float_as_int(rout[0]), __float_as_int(rout[1]),
+                                                   __float_as_int(rout[2]), __float_as_int(rout[3])));
+            st_stream_v4(io.index + e0, make_int4(x02 & 0xFFFFu, x13 & 0xFFFFu, x02 >> 16, x13 >> 16));
+            st_stream_u32(io.terminated + e0, 0u);
+            st_stream_u32(io.truncated + e0, trunc_w);
+            st_stream_u32(io.unsafe + e0, 0u);
+            st_stream_u32(io.count + e0, count_w);
+            s0w = row0; s1w = row1;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) tin[e] = tout[e];
+        }
+    }
+    if (bad_bits & 0x40404040u) atomicOr(io.status, 1ull);
+    if (io.stats)
+        block_flush_stats_grid(st_count, st_trunc, st_reward,
+                               static_cast<unsigned long long>(io.end - io.begin) * static_cast<unsigned long long>(mio.n_steps),
+                               s_stats, io.stats);
+    if (threadIdx.x == 0 && io.done_ctr != nullptr && s_ctr.arrived == gridDim.x - 1) {
+        *io.done_ctr = 0u;
+        *const_cast<uint32_t *>(io.step_ctr) = s_ctr.step + static_cast<uint32_t>(mio.n_steps);
+    }
+}
+
 }  // namespace
 
 template <auto Kernel>
@@ -299,4 +444,12 @@ cudaError_t gc_launch_grid_step(const GridParams &gp, const StepIO &io, int rng_
 {
     return rng_mode == GC_RNG_REPLAY ? launch_grid<GC_RNG_REPLAY>(gp, io, n_sm, st)
                                      : launch_grid<GC_RNG_PHILOX>(gp, io, n_sm, st);
+}
+
+cudaError_t gc_launch_grid_many(const GridParams &gp, const ManyIO &mio, int n_sm, cudaStream_t st)
+{
+    cudaError_t err = cudaSuccess;
+    const int g = grid_blocks<grid_many_kernel>(mio.io.end - mio.io.begin, n_sm, kGridSmemBytes, &err);
+    if (err != cudaSuccess) return err;
+    return launch_step_kernel(grid_many_kernel, g, kGridThreads, kGridSmemBytes, st, gp, mio);
 }

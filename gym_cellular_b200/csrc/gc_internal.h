@@ -41,6 +41,15 @@ struct StepIO {
     int32_t  max_episode_steps;
 };
 
+// gc_step_many in ONE launch (gc_cell_fast.cu: cell_pair_many_kernel; gc_grid.cu: grid_many_kernel): the bound
+// steps of a handle whose slots share every buffer but the actions
+struct ManyIO {
+    StepIO io;                                  // the shared buffers (io.actions is not used)
+    const int8_t *tape[GC_MAX_BINDINGS];        // actions of step k: tape[k % n_tape]
+    int32_t n_tape, n_steps;
+};
+#define GC_MANY_MAX_CELLS 8
+
 // Packed layout (gc_cell_packed.cu): ONE 32-bit word per env for the state and one for the action, 2 bits per
 // cell (cell c in bits 2c, 2c+1; n_states, n_actions <= 4).  For n_states == 4 the state word IS the tabular
 // index.  Per-env outputs shrink to reward + one flag byte.
@@ -143,6 +152,9 @@ cudaError_t gc_launch_cell_step(const CellTables &tab, const StepIO &io, int rng
 #define GC_PAIR_LUT_ENTRIES (GC_PAIR_LUT_PAIRS + 32)
 cudaError_t gc_launch_cell_pair_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int rng_mode,
                                      int n_sm, cudaStream_t stream);
+cudaError_t gc_launch_grid_many(const GridParams &gp, const ManyIO &mio, int n_sm, cudaStream_t stream);
+cudaError_t gc_launch_cell_pair_many(const CellTables &tab, const ManyIO &mio, const uint2 *lut, int rng_mode, int n_sm,
+                                     cudaStream_t stream);
 // TMA bulk-staged variant of the deterministic pair-table step for wide envs (gc_cell_tma.cu)
 cudaError_t gc_launch_cell_tma_step(const CellTables &tab, const StepIO &io, const uint2 *lut, int n_sm,
                                     cudaStream_t stream);

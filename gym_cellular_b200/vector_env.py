@@ -476,7 +476,9 @@ class CellularVectorEnv(gym.vector.VectorEnv):
         """`n_steps` pre-bound steps back to back in ONE foreign call (gc_step_many): step i launches the
         binding `slots[i % len(slots)]` (slots from `_bind` / `bind_step(...).slot`).  The launches are
         chained by programmatic dependent launch and no Python runs between them -- the per-step loop of
-        launch-bound batch sizes without capturing a CUDA graph."""
+        launch-bound batch sizes without capturing a CUDA graph.  Shards of up to 2^21 envs whose slots differ only
+        in their action tensors (what `_bind` / `bind_step` produce) run all the steps inside ONE kernel, every
+        per-step output still written at every step (include/gym_cellular_b200.h: gc_step_many)."""
         arr = self._slot_array(slots)
         st = (torch.cuda.current_stream(self.device) if stream is None else stream).cuda_stream
         _lib.check(self._lib.gc_step_many(self._h, arr, len(arr), int(n_steps), st))

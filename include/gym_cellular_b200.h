@@ -205,7 +205,15 @@ int gc_step_bound(gc_env *env, int32_t slot, void *stream);
  * launch-bound batch sizes (BASELINE configs 2 and 3).  Same kernels, same results, same statistics.
  * Shards above 2^21 envs always take plain launches (their kernels are long enough to hide the host calls).
  * gc_prepare_step_many builds the graph of a slot list ahead of time (no step is executed), so that the first
- * gc_step_many does not pay for the capture. */
+ * gc_step_many does not pay for the capture.
+ * ONE launch for all n_steps: when the slots of the list are int8 bindings that differ only in their action
+ * buffers (one set of in-place state / output arrays, a ring of action buffers), the shard has at most 2^21 envs
+ * (cellular: levels and actions <= 4, at most 8 cells; or grid world) and no final-observation buffer is set, the
+ * steps run inside a single kernel: the thread that owns an env keeps its state and episode step in registers
+ * from one step to the next and writes EVERY per-step output (state, t, reward, index, flags, side-effect row,
+ * statistics) at every step, as the separate launches would; results are bit-identical to them.  Only the
+ * launch gaps and the re-read of state and t go away (a 65,536-env step is a 3 us launch around 0.6 us of work).
+ * GC_B200_STEP_MANY_FUSED=0 in the environment (read at every call) keeps the separate launches. */
 int gc_step_many(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t n_steps, void *stream);
 int gc_prepare_step_many(gc_env *env, const int32_t *slots, int32_t n_slots);
 

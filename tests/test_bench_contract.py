@@ -32,10 +32,15 @@ def test_reference_arm_line():
 def test_native_arm_line():
     d = _run("--steps", "30", "--warmup", "3", "--workload", "cfg2", "--no-extra")
     assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks"} <= d.keys() and "impl" not in d
-    assert d["gpu_launches"] == 30 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["data"] == "synthetic"
+    # a 65,536-env shard: the 30 bound steps of the gc_step_many call run inside one kernel, and the same loop is
+    # reported with one launch per step beside it
+    assert d["gpu_launches"] == 1 and d["steps_per_launch"] == 30 and d["separate_launches"]["gpu_launches"] == 30
+    assert 0 < d["separate_launches"]["value"] < d["value"] and d["episode_stats"]["consistent"]
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["data"] == "synthetic"
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["bytes_per_env_step"] == 29.0 and r["algorithmic_bytes_per_launch"] == 29 * 65536
+    assert r["bytes_per_env_step"] == 29.0 and r["algorithmic_bytes_per_step"] == 29 * 65536
+    assert r["algorithmic_bytes_per_launch"] == 30 * 29 * 65536
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 4 * 65536 and e["d2h_bytes_per_step"] == 13 * 65536 and 0 < e["value"] < d["value"]
     assert d["clocks"]["sm_max_mhz"] and not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
