@@ -712,6 +712,7 @@ int gc_prepare_step_many(gc_env *env, const int32_t *slots, int32_t n_slots)
         if (slots[i] < 0 || slots[i] >= GC_MAX_BINDINGS || !env->bound_set[slots[i]])
             return fail(GC_ERR_INVALID, "no binding in slot %d", slots[i]);
     GC_ON_DEVICE(env->cfg.device);
+    if (n_slots <= GC_MAX_BINDINGS && many_fusable(env, slots, n_slots)) return GC_OK;     // one launch for all steps: no graph needed
     if (many_graphs_enabled(env) && n_slots >= 2) many_graph(env, slots, n_slots);   // best effort: plain launches otherwise
     return GC_OK;
 }
