@@ -604,8 +604,10 @@ def ncu_traffic(workload):
     return None
 
 
-def roofline_of(workload, batches, step_s, tag=None):
-    alg_bytes = sum(b["bytes"] * b["n"] for b in batches)           # per step, per rank
+def roofline_of(workload, batches, step_s, tag=None, resident_state=False):
+    # resident_state: the many-step kernel keeps state and episode step in registers between two steps, so a step
+    # moves C + 4 bytes per env less than SURVEY 8d's figure (it still writes both at every step)
+    alg_bytes = sum((b["bytes"] - (b["env"].n_cells + 4 if resident_state else 0)) * b["n"] for b in batches)   # per step, per rank
     n_rank = sum(b["n"] for b in batches)
     peak, peak_src = measured_peak()
     traffic = ncu_traffic(tag or workload)
@@ -698,7 +700,7 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
         "gpu_launches": launches * world,
         "host_us_per_launch": round(host_us, 2),
         "clocks": clocks,
-        "roofline": roofline_of(workload, batches, step_s),
+        "roofline": roofline_of(workload, batches, step_s, resident_state=sep_res is not None),
         "episode_stats": dict(totals, env_steps_expected=expect, consistent=stats_ok),
         "cuda_graph": graph_res,
         "fused_rollout": ro_res,
@@ -711,6 +713,8 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
         res["roofline"]["algorithmic_bytes_per_step"] = res["roofline"]["algorithmic_bytes_per_launch"]
         res["roofline"]["algorithmic_bytes_per_launch"] = int(res["roofline"]["algorithmic_bytes_per_launch"] * spl)
         res["roofline"]["kernels_per_step"] = round(len(batches) / spl, 4)
+        res["roofline"]["bytes_note"] = ("state and t are read once per launch, not once per step: the step's algorithmic bytes are "
+                                         "SURVEY 8d's 3C + 20 minus C + 4")
         res["step_many"] = ("bound steps of one gc_step_many call run inside ONE kernel (shards <= 2^21 envs): state and episode "
                             "step in registers between the steps, actions read and every per-step output written at every step; "
                             "bit-identical to separate launches (tests/test_gpu_many.py); `separate_launches` = the same loop with "
