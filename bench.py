@@ -607,7 +607,9 @@ def ncu_traffic(workload):
 def roofline_of(workload, batches, step_s, tag=None, resident_state=False):
     # resident_state: the many-step kernel keeps state and episode step in registers between two steps, so a step
     # moves C + 4 bytes per env less than SURVEY 8d's figure (it still writes both at every step)
-    alg_bytes = sum((b["bytes"] - (b["env"].n_cells + 4 if resident_state else 0)) * b["n"] for b in batches)   # per step, per rank
+    def not_reread(b):                       # state + t: one packed word + 4, or C bytes + 4
+        return 8 if (b["packed"] and b["kind"] == "cellular") else b["env"].n_cells + 4
+    alg_bytes = sum((b["bytes"] - (not_reread(b) if resident_state else 0)) * b["n"] for b in batches)   # per step, per rank
     n_rank = sum(b["n"] for b in batches)
     peak, peak_src = measured_peak()
     traffic = ncu_traffic(tag or workload)
@@ -733,7 +735,9 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
                          "gpu_launches": p_launches * world, "host_us_per_launch": round(p_host_us, 2),
                          "layout": "cellular sub-batches: one 32-bit word per env for the state, one for the action "
                                    "(2 bits per cell), reward + one flag byte out",
-                         "roofline": roofline_of(workload, pbatches, p_ms * 1e-3 / steps, tag=workload + "_packed")}
+                         "steps_per_launch": round(steps * len(pbatches) / max(p_launches, 1), 1),
+                         "roofline": roofline_of(workload, pbatches, p_ms * 1e-3 / steps, tag=workload + "_packed",
+                                                 resident_state=p_launches < steps * len(pbatches))}
     el_host, h2d, d2h = time_host_path(pbatches, e2e_steps, 2, dist, device)
     res["e2e"] = {"value": world * n_rank * e2e_steps / el_host, "unit": "env-steps/s",
                   "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
@@ -858,7 +862,7 @@ def main():
                             "step_many": r.get("step_many"),
                             "fused_rollout": r["fused_rollout"], "episode_stats_consistent": r["episode_stats"]["consistent"],
                             "packed": None if "packed" not in r else
-                            {k: r["packed"][k] for k in ("value", "ms_per_step")} | {"roofline_frac": r["packed"]["roofline"]["frac"],
+                            {k: r["packed"][k] for k in ("value", "ms_per_step", "steps_per_launch")} | {"roofline_frac": r["packed"]["roofline"]["frac"],
                                                                                     "bytes_per_env_step": r["packed"]["roofline"]["bytes_per_env_step"]}}
     pcie = measure_pcie(device, dist)
     check = shard_check(dist, device, rank, world) if dist is not None else None

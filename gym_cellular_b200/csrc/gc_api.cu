@@ -670,8 +670,20 @@ bool many_fusable(const gc_env *env, const int32_t *slots, int32_t n_slots)
     if (env->cfg.kind == GC_KIND_CELLULAR) {
         if (!env->fast_ok || env->cfg.n_cells > GC_MANY_MAX_CELLS) return false;
     }
+    const int layout = env->bound_set[slots[0]];             // 1: int8 bindings, 2: packed bindings
     for (int32_t i = 0; i < n_slots; ++i)
-        if (env->bound_set[slots[i]] != 1) return false;
+        if (env->bound_set[slots[i]] != layout) return false;
+    if (layout == 2) {
+        if (env->cfg.kind != GC_KIND_CELLULAR) return false;
+        const PackedIO &a = env->bound_packed[slots[0]];
+        for (int32_t i = 1; i < n_slots; ++i) {
+            const PackedIO &b = env->bound_packed[slots[i]];
+            if (a.state != b.state || a.t != b.t || a.reward != b.reward || a.index != b.index || a.flags != b.flags ||
+                a.se_row != b.se_row || a.stats != b.stats || a.final_state != b.final_state)
+                return false;
+        }
+        return a.final_state == nullptr;
+    }
     const StepIO &a = env->bound[slots[0]];
     for (int32_t i = 1; i < n_slots; ++i) {
         const StepIO &b = env->bound[slots[i]];
@@ -687,13 +699,26 @@ constexpr int32_t kManyFusedMaxSteps = 4096;       // steps per launch
 
 int launch_many_fused(gc_env *env, const int32_t *slots, int32_t n_slots, int32_t first, int32_t n_steps, cudaStream_t st)
 {
+    const bool draws = (env->cfg.flags & GC_F_NOISE) && env->tab.noise_thr_nz;
+    if (env->bound_set[slots[0]] == 2) {
+        PackedManyIO pio;
+        pio.io = env->bound_packed[slots[0]];
+        for (int32_t i = 0; i < GC_MAX_BINDINGS; ++i)
+            pio.tape[i] = i < n_slots ? env->bound_packed[slots[(first + i) % n_slots]].actions : nullptr;
+        pio.n_tape = n_slots;
+        pio.n_steps = n_steps;
+        const cudaError_t e = gc_launch_cell_packed_many(env->tab, pio, env->d_packed_lut, draws, env->n_sm, st);
+        if (e != cudaSuccess) return fail(GC_ERR_CUDA, "many-step kernel launch failed: %s", cudaGetErrorString(e));
+        env->launches += 1;
+        env->global_step += n_steps;
+        return GC_OK;
+    }
     ManyIO mio;
     mio.io = env->bound[slots[0]];
     for (int32_t i = 0; i < n_slots; ++i) mio.tape[i] = env->bound[slots[(first + i) % n_slots]].actions;
     for (int32_t i = n_slots; i < GC_MAX_BINDINGS; ++i) mio.tape[i] = nullptr;
     mio.n_tape = n_slots;
     mio.n_steps = n_steps;
-    const bool draws = (env->cfg.flags & GC_F_NOISE) && env->tab.noise_thr_nz;
     const cudaError_t e = env->cfg.kind == GC_KIND_CELLULAR
         ? gc_launch_cell_pair_many(env->tab, mio, env->d_pair_lut, draws ? GC_RNG_PHILOX : GC_RNG_NONE, env->n_sm, st)
         : gc_launch_grid_many(env->grid, mio, env->n_sm, st);

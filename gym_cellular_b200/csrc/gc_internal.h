@@ -72,6 +72,12 @@ struct PackedIO {
     int32_t episodic, max_episode_steps;
 };
 
+struct PackedManyIO {                           // gc_step_many in one launch, packed bindings (gc_cell_packed.cu)
+    PackedIO io;                                // the shared buffers (io.actions is not used)
+    const uint32_t *tape[GC_MAX_BINDINGS];      // action words of step k: tape[k % n_tape]
+    int32_t n_tape, n_steps;
+};
+
 // K-step fused rollout (gc_rollout.cu): state stays in registers for n_steps steps, actions are
 // generated in the kernel (uniformly random, or from a tabular policy).
 struct RolloutIO {
@@ -170,6 +176,8 @@ cudaError_t gc_launch_cell_pair8_step(const CellTables &tab, const StepIO &io, c
 void gc_build_packed_lut(const gc_cell_tables *t, int C, int S, int A, bool noise, uint2 *lut);
 cudaError_t gc_launch_cell_packed_step(const CellTables &tab, const PackedIO &io, const uint2 *lut, bool noise,
                                        int n_sm, cudaStream_t stream);
+cudaError_t gc_launch_cell_packed_many(const CellTables &tab, const PackedManyIO &mio, const uint2 *lut, bool noise, int n_sm,
+                                       cudaStream_t stream);
 cudaError_t gc_launch_reset_packed(uint32_t init_packed, uint32_t init_index, const uint8_t *mask, uint32_t *state,
                                    int32_t *t, uint32_t *index, int64_t n, cudaStream_t stream);
 cudaError_t gc_launch_pack(int64_t n, int64_t ld, int n_cells, const int8_t *cells, uint32_t *packed, cudaStream_t stream);

@@ -206,7 +206,7 @@ int gc_step_bound(gc_env *env, int32_t slot, void *stream);
  * Shards above 2^21 envs always take plain launches (their kernels are long enough to hide the host calls).
  * gc_prepare_step_many builds the graph of a slot list ahead of time (no step is executed), so that the first
  * gc_step_many does not pay for the capture.
- * ONE launch for all n_steps: when the slots of the list are int8 bindings that differ only in their action
+ * ONE launch for all n_steps: when the slots of the list are bindings of one layout that differ only in their action
  * buffers (one set of in-place state / output arrays, a ring of action buffers), the shard has at most 2^21 envs
  * (cellular: levels and actions <= 4, at most 8 cells; or grid world) and no final-observation buffer is set, the
  * steps run inside a single kernel: the thread that owns an env keeps its state and episode step in registers

@@ -168,3 +168,59 @@ def test_slots_with_their_own_outputs_stay_on_separate_launches(B, O):
         ora.step(acts[i % 2])
     assert (host(env.state) == ora.state).all()
     np.testing.assert_allclose(host(own_reward[:n]), ora.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)    # step 6 used slot s1
+
+
+def pack_host(cells):
+    w = np.zeros(cells.shape[1], np.uint32)
+    for c in range(cells.shape[0]):
+        w |= cells[c].astype(np.uint32) << np.uint32(2 * c)
+    return w
+
+
+@pytest.mark.parametrize("C,S,stochastic,episodic,se,limit,n", [
+    (3, 3, False, True, False, 0, 65536), (3, 3, True, False, True, 5, 20011), (4, 4, True, True, False, 6, 9001),
+    (8, 4, True, False, True, 7, 2049), (1, 2, False, True, False, 3, 33), (7, 4, False, True, False, 0, 5003)])
+def test_packed_many_steps_in_one_launch(B, O, C, S, stochastic, episodic, se, limit, n):
+    """The same for packed bindings (cell_packed_many_kernel): bit-identical to separate launches of a twin handle and
+    to the int8 layout stepped through the oracle."""
+    kw = dict(num_envs=n, n_cells=C, n_states=S, stochastic=stochastic, rng_episodic=episodic, env_seed=C + S,
+              max_episode_steps=limit or None, emit_side_effects=se, env_id_offset=4 * 1000003)
+    fused = B.PackedCellularVectorEnv(**kw)
+    plain = B.PackedCellularVectorEnv(emit_final_obs=True, **kw)           # a final-observation buffer keeps it off the fused path
+    ora = O.OracleEnv(n_envs=n, n_cells=C, n_states=S, noise=stochastic, rng_episodic=episodic, seed=C + S, max_episode_steps=limit,
+                      env_id_offset=4 * 1000003, reward="nonlinear_rp" if stochastic else "right_polarizing")
+    rng = np.random.default_rng(n)
+    acts = [rng.integers(0, S, size=(C, n)).astype(np.int8) for _ in range(4)]
+
+    def ring(env):
+        out = []
+        for a in acts:
+            w = torch.zeros(env.ld, dtype=torch.int32, device="cuda")
+            w[:n] = dev(pack_host(a).view(np.int32))
+            out.append(w)
+        return out
+    slots_f = [fused._bind(w) for w in ring(fused)]
+    slots_p = [plain._bind(w) for w in ring(plain)]
+    done = 0
+    for steps in (9, 6):
+        l_f, l_p = fused.launch_count, plain.launch_count
+        fused.step_many([slots_f[(done + i) % 4] for i in range(4)], steps)
+        plain.step_many([slots_p[(done + i) % 4] for i in range(4)], steps)
+        assert fused.launch_count - l_f == 1 and plain.launch_count - l_p == steps
+        for i in range(steps):
+            ora.step(acts[(done + i) % 4])
+        done += steps
+        assert torch.equal(fused._state, plain._state) and torch.equal(fused._t, plain._t)
+        assert torch.equal(fused._reward[:n], plain._reward[:n]) and torch.equal(fused._flags[:n], plain._flags[:n])
+        if fused._index_ptr() is not None:
+            assert torch.equal(fused.tabular_state(), plain.tabular_state())
+        if se:
+            assert torch.equal(fused._se_row[:n], plain._se_row[:n])
+        assert fused.stats() == plain.stats()
+        assert (host(fused._state[:n]).view(np.uint32) == pack_host(ora.state)).all() and (host(fused._t[:n]) == ora.t).all()
+        assert (host(fused.tabular_state()) == ora.index).all()
+        np.testing.assert_allclose(host(fused._reward[:n]), ora.reward, rtol=REWARD_RTOL, atol=REWARD_ATOL)
+        assert fused.sync_step_counter() == done
+    s = fused.stats()
+    assert s["env_steps"] == done * n == ora.stats[0] and s["unsafe_steps"] == ora.stats[1] and s["count_sum"] == ora.stats[2]
+    assert s["episodes_truncated"] == ora.stats[3]

@@ -297,7 +297,10 @@ def test_step_many_bound_and_graph(B, O):
     packed layout with non-episodic noise: 3 x 8 distinct steps, all reading the device-resident counter."""
     import ctypes as C
     n = 10007
-    env = B.PackedCellularVectorEnv(num_envs=n, n_cells=4, n_states=4, stochastic=True, rng_episodic=False, env_seed=9)
+    # (a final-observation buffer keeps the handle on separate launches: the one-launch path of small shards is
+    # covered by tests/test_gpu_many.py)
+    env = B.PackedCellularVectorEnv(num_envs=n, n_cells=4, n_states=4, stochastic=True, rng_episodic=False, env_seed=9,
+                                    emit_final_obs=True)
     ora = O.OracleEnv(n_envs=n, n_cells=4, n_states=4, noise=True, rng_episodic=False, seed=9, reward="nonlinear_rp")
     rng = np.random.default_rng(5)
     acts = [rng.integers(0, 4, size=(4, n)).astype(np.int8) for _ in range(8)]
