@@ -715,6 +715,12 @@ def bench_workload(workload, steps, warmup, dist, device, world, rank, e2e_steps
         res["roofline"]["algorithmic_bytes_per_step"] = res["roofline"]["algorithmic_bytes_per_launch"]
         res["roofline"]["algorithmic_bytes_per_launch"] = int(res["roofline"]["algorithmic_bytes_per_launch"] * spl)
         res["roofline"]["kernels_per_step"] = round(len(batches) / spl, 4)
+        # DRAM bytes of one launch of the many-step kernel (ncu capture of a 64-step launch, profiles/r02_kernel_*_many.md)
+        many_traffic = ncu_traffic(workload + "_many")
+        res["roofline"]["traffic"] = many_traffic
+        res["roofline"]["dram_bytes_over_algorithmic"] = (
+            None if not isinstance(many_traffic, (int, float)) else
+            round(many_traffic / (res["roofline"]["algorithmic_bytes_per_step"] * STATS_EVERY), 3))
         res["roofline"]["bytes_note"] = ("state and t are read once per launch, not once per step: the step's algorithmic bytes are "
                                          "SURVEY 8d's 3C + 20 minus C + 4")
         res["step_many"] = ("bound steps of one gc_step_many call run inside ONE kernel (shards <= 2^21 envs): state and episode "
