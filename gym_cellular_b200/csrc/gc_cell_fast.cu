@@ -356,8 +356,11 @@ cudaError_t launch_pair_cr(const CellTables &tab, const StepIO &io, const uint2 
 // EVERY per-step output (state, t, reward, index, flags, side-effect row, statistics) is written at every step
 // exactly as the n_steps separate launches write it -- same do_cells, same epilogue, same Philox counters
 // (global step of the launch + k) -- so the results are bit-identical to them (tests/test_gpu_many.py).
-template <int C, int RNG, bool WITH_SE>
-__global__ void __launch_bounds__(kThreads, 2)
+#ifndef GC_MANY_SMALL_THREADS
+#define GC_MANY_SMALL_THREADS 64
+#endif
+template <int C, int RNG, bool WITH_SE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 256 / THREADS * 2)
 cell_pair_many_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ ManyIO mio, const uint2 *__restrict__ lut)
 {
     const StepIO &io = mio.io;
@@ -370,10 +373,10 @@ cell_pair_many_kernel(const __grid_constant__ CellTables tab, const __grid_const
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
 
-    for (int i = threadIdx.x; i < N_PAIR; i += kThreads) s_pair[i] = lut[i];
+    for (int i = threadIdx.x; i < N_PAIR; i += THREADS) s_pair[i] = lut[i];
     if (threadIdx.x < N_SINGLE) s_single[threadIdx.x] = lut[GC_PAIR_LUT_PAIRS + threadIdx.x];
     if (WITH_SE)
-        for (int i = threadIdx.x; i < C * GC_TBL; i += kThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
+        for (int i = threadIdx.x; i < C * GC_TBL; i += THREADS) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     pdl_launch_dependents();
     pdl_wait();
@@ -382,11 +385,11 @@ cell_pair_many_kernel(const __grid_constant__ CellTables tab, const __grid_const
     const uint32_t step0 = step_counter_arrive(io, &s_ctr);
 
     const uint32_t ld = static_cast<uint32_t>(io.ld);
-    const uint32_t stride = gridDim.x * kThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
+    const uint32_t stride = gridDim.x * THREADS * kEPT, e_end = static_cast<uint32_t>(io.end);
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
     long long st_reward = 0;
 #pragma unroll 1
-    for (uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kThreads + threadIdx.x) * kEPT; e0 < e_end; e0 += stride) {
+    for (uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * THREADS + threadIdx.x) * kEPT; e0 < e_end; e0 += stride) {
         const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
         const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
@@ -484,13 +487,27 @@ cell_pair_many_kernel(const __grid_constant__ CellTables tab, const __grid_const
     }
 }
 
+template <int C, int RNG, bool WITH_SE, int THREADS>
+cudaError_t launch_pair_many_t(const CellTables &tab, const ManyIO &mio, const uint2 *lut, int n_sm, cudaStream_t st)
+{
+    const int64_t n = mio.io.end - mio.io.begin;
+    return launch_step_kernel(cell_pair_many_kernel<C, RNG, WITH_SE, THREADS>,
+                              grid_for<cell_pair_many_kernel<C, RNG, WITH_SE, THREADS>, THREADS>(n, n_sm), THREADS, 0, st, tab, mio, lut);
+}
+
+// Shards that do not fill every SM with 256-thread blocks (65,536 envs = 64 of them) are spread over more SMs with
+// 64-thread blocks: the steps of such a shard are bound by the dependent-instruction latency of its warps
+// (config 2, same box: 99-106 G env-steps/s with 256-thread blocks, 117-140 with 128, 132 with 64; packed 113-122 / 117-120 / 127-128).
 template <int C, int RNG>
 cudaError_t launch_pair_many_cr(const CellTables &tab, const ManyIO &mio, const uint2 *lut, int n_sm, cudaStream_t st)
 {
     const int64_t n = mio.io.end - mio.io.begin;
+    const bool small = (n + kThreads * kEPT - 1) / (kThreads * kEPT) < n_sm;
     if (mio.io.se_row)
-        return launch_step_kernel(cell_pair_many_kernel<C, RNG, true>, grid_for<cell_pair_many_kernel<C, RNG, true>>(n, n_sm), kThreads, 0, st, tab, mio, lut);
-    return launch_step_kernel(cell_pair_many_kernel<C, RNG, false>, grid_for<cell_pair_many_kernel<C, RNG, false>>(n, n_sm), kThreads, 0, st, tab, mio, lut);
+        return small ? launch_pair_many_t<C, RNG, true, GC_MANY_SMALL_THREADS>(tab, mio, lut, n_sm, st)
+                     : launch_pair_many_t<C, RNG, true, kThreads>(tab, mio, lut, n_sm, st);
+    return small ? launch_pair_many_t<C, RNG, false, GC_MANY_SMALL_THREADS>(tab, mio, lut, n_sm, st)
+                 : launch_pair_many_t<C, RNG, false, kThreads>(tab, mio, lut, n_sm, st);
 }
 
 template <int C>

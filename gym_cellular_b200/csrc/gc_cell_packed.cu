@@ -274,8 +274,11 @@ cell_packed_kernel(const __grid_constant__ CellTables tab, const __grid_constant
 // k is computed, every per-step output is written at every step by the same packed_word as the step kernel (so
 // the results are bit-identical to n_steps launches), and the table is always replicated: its staging is paid
 // once per launch.
-template <int C, int RNG, bool EXTRA>
-__global__ void __launch_bounds__(kPackThreads, 2)
+#ifndef GC_MANY_SMALL_THREADS
+#define GC_MANY_SMALL_THREADS 64
+#endif
+template <int C, int RNG, bool EXTRA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 256 / THREADS * 2)
 cell_packed_many_kernel(const __grid_constant__ CellTables tab, const __grid_constant__ PackedManyIO mio,
                         const uint2 *__restrict__ lut, const int REP_LOG2)
 {
@@ -288,11 +291,11 @@ cell_packed_many_kernel(const __grid_constant__ CellTables tab, const __grid_con
     __shared__ unsigned long long s_stats[5];
     __shared__ StepCounterShared s_ctr;
     const uint32_t REP = 1u << REP_LOG2;
-    const uint32_t stride = gridDim.x * kPackThreads * kEPT, e_end = static_cast<uint32_t>(io.end);
-    for (int i = threadIdx.x; i < (N_PAIR << REP_LOG2); i += kPackThreads) s_pair[i] = lut[i >> REP_LOG2];
-    for (int i = threadIdx.x; i < (N_SINGLE << REP_LOG2); i += kPackThreads) s_single[i] = lut[GC_PAIR_LUT_PAIRS + (i >> REP_LOG2)];
+    const uint32_t stride = gridDim.x * THREADS * kEPT, e_end = static_cast<uint32_t>(io.end);
+    for (int i = threadIdx.x; i < (N_PAIR << REP_LOG2); i += THREADS) s_pair[i] = lut[i >> REP_LOG2];
+    for (int i = threadIdx.x; i < (N_SINGLE << REP_LOG2); i += THREADS) s_single[i] = lut[GC_PAIR_LUT_PAIRS + (i >> REP_LOG2)];
     if (EXTRA && io.se_row)
-        for (int i = threadIdx.x; i < C * GC_TBL; i += kPackThreads) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
+        for (int i = threadIdx.x; i < C * GC_TBL; i += THREADS) s_se[i / GC_TBL][i % GC_TBL] = tab.se[i / GC_TBL][i % GC_TBL];
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0;
     pdl_launch_dependents();
     pdl_wait();
@@ -307,7 +310,7 @@ cell_packed_many_kernel(const __grid_constant__ CellTables tab, const __grid_con
     uint32_t st_steps = 0, st_unsafe = 0, st_count = 0, st_trunc = 0;
     long long st_reward = 0;
 #pragma unroll 1
-    for (uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * kPackThreads + threadIdx.x) * kEPT; e0 < e_end; e0 += stride) {
+    for (uint32_t e0 = static_cast<uint32_t>(io.begin) + (blockIdx.x * THREADS + threadIdx.x) * kEPT; e0 < e_end; e0 += stride) {
         const int rem = static_cast<int>(e_end - e0 < kEPT ? e_end - e0 : kEPT);
         const uint64_t gid0 = static_cast<uint64_t>(io.env_id_offset) + e0;
         const uint32_t gid_lo = static_cast<uint32_t>(gid0), gid_hi = static_cast<uint32_t>(gid0 >> 32);
@@ -340,20 +343,30 @@ cell_packed_many_kernel(const __grid_constant__ CellTables tab, const __grid_con
     }
 }
 
-template <int C, int RNG, bool EXTRA>
-cudaError_t launch_packed_many_cre(const CellTables &tab, const PackedManyIO &mio, const uint2 *lut, int n_sm, cudaStream_t st)
+template <int C, int RNG, bool EXTRA, int THREADS>
+cudaError_t launch_packed_many_t(const CellTables &tab, const PackedManyIO &mio, const uint2 *lut, int n_sm, cudaStream_t st)
 {
-    const auto kernel = cell_packed_many_kernel<C, RNG, EXTRA>;
+    const auto kernel = cell_packed_many_kernel<C, RNG, EXTRA, THREADS>;
     const int64_t n = mio.io.end - mio.io.begin;
     const size_t smem = packed_smem_bytes(RNG, true);
     static int per_sm = 0;
     if (per_sm == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPackThreads, smem) != cudaSuccess || per_sm < 1))
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem) != cudaSuccess || per_sm < 1))
         per_sm = 1;
-    const int64_t need = (n + kPackThreads * kEPT - 1) / (kPackThreads * kEPT);
+    const int64_t need = (n + THREADS * kEPT - 1) / (THREADS * kEPT);
     const int64_t cap = static_cast<int64_t>(n_sm) * per_sm;
     const int grid = static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
-    return launch_step_kernel(kernel, grid, kPackThreads, smem, st, tab, mio, lut, packed_rep_log2(RNG, true));
+    return launch_step_kernel(kernel, grid, THREADS, smem, st, tab, mio, lut, packed_rep_log2(RNG, true));
+}
+
+// shards that do not fill every SM with 256-thread blocks take smaller blocks (see cell_pair_many_kernel's launcher)
+template <int C, int RNG, bool EXTRA>
+cudaError_t launch_packed_many_cre(const CellTables &tab, const PackedManyIO &mio, const uint2 *lut, int n_sm, cudaStream_t st)
+{
+    const int64_t n = mio.io.end - mio.io.begin;
+    const bool small = (n + kPackThreads * kEPT - 1) / (kPackThreads * kEPT) < n_sm;
+    return small ? launch_packed_many_t<C, RNG, EXTRA, GC_MANY_SMALL_THREADS>(tab, mio, lut, n_sm, st)
+                 : launch_packed_many_t<C, RNG, EXTRA, kPackThreads>(tab, mio, lut, n_sm, st);
 }
 
 template <int C, int RNG>
